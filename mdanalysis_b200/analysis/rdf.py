@@ -1,0 +1,216 @@
+"""InterRDF on the GPU -- mirror of ``MDAnalysis/analysis/rdf.py`` (:86-348).
+
+Per frame the reference does ``capped_distance(g1, g2, r_max, box)`` followed by
+``np.histogram`` (rdf.py:268-291).  Here all frames of the block are binned by
+ONE call of ``mdagpu_rdf_accumulate``; no pair list is ever materialised.
+
+Exactness: for every frame the host decides which algorithm the reference would
+have used (``lib.distances._determine_method``), because brute force and FastNS
+differ in their minimum-image arithmetic; the kernel then evaluates the float64
+squared distance of that algorithm bit for bit and compares it with thresholds
+that are the exact pre-images of np.histogram's float64 edges under sqrt.  The
+integer counts therefore equal the reference's.
+"""
+import numpy as np
+
+from .._cabi import (DEVICE, HOST, MIC_ORTHO_LAZY, MIC_ORTHO_ROUND, MIC_TRICLINIC, check,
+                     current_stream, is_tensor, load, ptr, tensor_ptr)
+from ..frames import as_block
+from ..lib.distances import _determine_method
+from ..lib.mdamath import box_volume, triclinic_vectors
+from .base import BlockAnalysis
+
+
+def sqrt_ge_threshold(e):
+    """Smallest float64 x with sqrt(x) >= e  (sqrt correctly rounded, monotone)."""
+    e = np.float64(e)
+    if e <= 0.0:
+        return np.float64(0.0)
+    x = e * e
+    while np.sqrt(x) >= e:
+        x = np.nextafter(x, -np.inf)
+    while np.sqrt(x) < e:
+        x = np.nextafter(x, np.inf)
+    return x
+
+
+def sqrt_le_threshold(e):
+    """Largest float64 x with sqrt(x) <= e."""
+    e = np.float64(e)
+    if e < 0.0:
+        return np.float64(-1.0)
+    x = e * e
+    while np.sqrt(x) <= e:
+        x = np.nextafter(x, np.inf)
+    while np.sqrt(x) > e:
+        x = np.nextafter(x, -np.inf)
+    return x
+
+
+def histogram_thresholds(edges):
+    """d2 thresholds equivalent to binning sqrt(d2) with np.histogram on ``edges``."""
+    t = np.empty(len(edges), dtype=np.float64)
+    for k, e in enumerate(edges[:-1]):
+        t[k] = sqrt_ge_threshold(e)
+    t[-1] = sqrt_le_threshold(edges[-1])
+    return t
+
+
+class InterRDF(BlockAnalysis):
+    """Radial distribution function between two groups of atoms.
+
+    g1, g2   FrameBlock | [F, n, 3] array / CUDA tensor | AtomGroup with the same
+             frames; pass the SAME object for a self RDF (pairs (i, i) are then
+             counted in bin 0 unless ``exclusion_block=(1, 1)``, as in the reference)
+    dimensions  unit cells [F, 6] / [6] when g1 is a bare array
+    nbins, range, norm ('rdf' | 'density' | 'none'), exclusion_block: as rdf.py:220-251
+    """
+
+    def __init__(self, g1, g2, nbins=75, range=(0.0, 15.0), norm="rdf", exclusion_block=None,
+                 exclude_same=None, dimensions=None, distributed=False, **kwargs):
+        b1 = as_block(g1, dimensions)
+        # distributed=True: this rank holds one shard of the frames; counts, volume
+        # and frame count are summed over ranks (NCCL all_reduce on the device
+        # histogram) before normalisation -- results.ndarray_sum of the reference.
+        self._distributed = distributed
+        super().__init__(b1, **kwargs)
+        self._same = g2 is g1 or g2 is None
+        self._b2 = b1 if self._same else as_block(g2, dimensions)
+        if self._b2.n_frames != b1.n_frames:
+            raise ValueError("g1 and g2 must have the same number of frames")
+        self.norm = str(norm).lower()
+        self.rdf_settings = {"bins": nbins, "range": range}
+        self._exclusion_block = exclusion_block
+        if exclude_same is not None:
+            if exclude_same not in ["residue", "segment", "chain"]:
+                raise ValueError("The exclude_same argument to InterRDF must be None, 'residue', "
+                                 "'segment' or 'chain'.")
+            if exclusion_block is not None:
+                raise ValueError("The exclude_same argument to InterRDF cannot be used with "
+                                 "exclusion_block.")
+            raise NotImplementedError("exclude_same is not available in the cuda backend yet; "
+                                      "use exclusion_block")
+        if self.norm not in ["rdf", "density", "none"]:
+            raise ValueError(f"'{self.norm}' is an invalid norm. Use 'rdf', 'density' or 'none'.")
+
+    def run(self, start=None, stop=None, step=None, frames=None, **kwargs):
+        idx = self._slice(start, stop, step, frames)
+        self._b2_run = self._b2 if self._same else self._b2.slice_frames(idx)
+        return super().run(start, stop, step, frames, **kwargs)
+
+    def _prepare(self, blk):
+        count, edges = np.histogram([-1], **self.rdf_settings)
+        count = count.astype(np.float64)
+        count *= 0.0
+        self.results.count = count
+        self.results.edges = edges
+        self.results.bins = 0.5 * (edges[:-1] + edges[1:])
+        self.volume_cum = 0
+        self._maxrange = self.rdf_settings["range"][1]
+
+    # -- per-frame method of the reference, grouped into as few launches as possible --
+    def _frame_modes(self, blk, na, nb):
+        dims = blk.dimensions
+        if dims is None:
+            raise ValueError("InterRDF on the cuda backend needs unit-cell dimensions "
+                             "(box=None frames are not supported)")
+        uniq = dims[:1] if blk.constant_box() else dims
+        modes = []
+        ra = np.empty((na, 3), dtype=np.float32)     # only the lengths matter when a box is given
+        rb = np.empty((nb, 3), dtype=np.float32)
+        for box in uniq:
+            method = _determine_method(ra, rb, self._maxrange, box=box)
+            h9 = triclinic_vectors(box).reshape(9)
+            if method == "nsgrid":
+                tri = bool(h9[3] != 0 or h9[6] != 0 or h9[7] != 0)          # nsgrid.pyx:319-321
+                modes.append((1, MIC_TRICLINIC if tri else MIC_ORTHO_LAZY, 1))
+            else:
+                ortho = bool(np.all(box[3:] == 90.0))                         # util.py:2522
+                modes.append((0, MIC_ORTHO_ROUND if ortho else MIC_TRICLINIC, 0 if ortho else 1))
+        if len(uniq) == 1:
+            modes = modes * blk.n_frames
+        return modes
+
+    def _compute(self, blk):
+        b2 = blk if self._same else self._b2_run
+        na, nb = blk.n_atoms, b2.n_atoms
+        nbins = len(self.results.edges) - 1
+        lo, hi = float(self.results.edges[0]), float(self.results.edges[-1])
+        thr = histogram_thresholds(self.results.edges)
+        xa, xb = self._exclusion_block if self._exclusion_block is not None else (0, 0)
+        modes = self._frame_modes(blk, na, nb)
+        dev = blk.on_device
+        if dev:
+            import torch
+            counts = torch.zeros(nbins, dtype=torch.int64, device=blk.positions.device)
+        else:
+            counts = np.zeros(nbins, dtype=np.uint64)
+        rc2 = float(self._maxrange) * float(self._maxrange)           # nsgrid.pyx:540
+        d2_brute = float(sqrt_le_threshold(self._maxrange))           # d <= max_cutoff
+        for mode in sorted(set(modes)):
+            use_grid, mic, wrap = mode
+            fidx = np.flatnonzero([m == mode for m in modes])
+            whole = len(fidx) == blk.n_frames
+            A = blk.positions if whole else blk.positions[fidx if not dev else torch.as_tensor(fidx, device=blk.positions.device)]
+            B = None if self._same else (b2.positions if whole else b2.positions[fidx if not dev else torch.as_tensor(fidx, device=blk.positions.device)])
+            dims = blk.dimensions if whole else blk.dimensions[fidx]
+            const = bool((dims == dims[0]).all())
+            box6 = np.ascontiguousarray(dims[:1] if const else dims, dtype=np.float32)
+            h9 = np.ascontiguousarray([triclinic_vectors(b).reshape(9) for b in box6], dtype=np.float32)
+            d2_max = rc2 if use_grid else d2_brute
+            if dev:
+                A = A.contiguous()
+                Bp = None if B is None else tensor_ptr(B.contiguous())
+                rc = load().mdagpu_rdf_accumulate(
+                    tensor_ptr(A), na, Bp, nb, len(fidx), ptr(box6), ptr(h9), int(not const), mic,
+                    wrap, float(self._maxrange), d2_max, use_grid, ptr(thr), nbins, lo, hi, int(xa),
+                    int(xb), tensor_ptr(counts), DEVICE, current_stream(A))
+            else:
+                A = np.ascontiguousarray(A)
+                B = None if B is None else np.ascontiguousarray(B)
+                rc = load().mdagpu_rdf_accumulate(
+                    ptr(A), na, ptr(B), nb, len(fidx), ptr(box6), ptr(h9), int(not const), mic, wrap,
+                    float(self._maxrange), d2_max, use_grid, ptr(thr), nbins, lo, hi, int(xa),
+                    int(xb), ptr(counts), HOST, None)
+            check(rc)
+        for box in blk.dimensions:                       # rdf.py:291, summed in frame order
+            self.volume_cum += box_volume(box)
+        if self._distributed:
+            counts = self._allreduce(counts, dev, blk)
+        self._device_counts = counts if dev else None
+        host_counts = counts.cpu().numpy() if dev else counts
+        self.results.count += host_counts.astype(np.float64)
+        self._nA, self._nB = na, nb
+
+    def _allreduce(self, counts, dev, blk):
+        """Sum histogram, cumulative volume and frame count over all ranks."""
+        import torch
+        from .. import parallel
+        if not parallel.is_distributed():
+            return counts
+        if not dev:
+            counts = torch.as_tensor(counts.astype(np.int64))
+            if torch.distributed.get_backend() == "nccl":
+                counts = counts.cuda()
+        meta = torch.tensor([float(self.volume_cum), float(self.n_frames)], dtype=torch.float64,
+                            device=counts.device)
+        parallel.allreduce_sum(counts)
+        parallel.allreduce_sum(meta)
+        self.volume_cum = float(meta[0])
+        self.n_frames = int(round(float(meta[1])))
+        return counts if dev else counts.cpu().numpy().astype(np.uint64)
+
+    def _conclude(self):
+        norm = self.n_frames
+        if self.norm in ["rdf", "density"]:
+            vols = np.power(self.results.edges, 3)
+            norm = norm * (4 / 3 * np.pi * np.diff(vols))
+        if self.norm == "rdf":
+            N = self._nA * self._nB
+            if self._exclusion_block:
+                xA, xB = self._exclusion_block
+                nblocks = self._nA / xA
+                N -= xA * xB * nblocks
+            box_vol = self.volume_cum / self.n_frames
+            norm = norm * (N / box_vol)
+        self.results.rdf = self.results.count / norm

@@ -1,0 +1,253 @@
+// engine.cuh -- cell-list build and the cutoff pair traversal shared by FastNS,
+// capped distances, InterRDF and contacts.
+//
+// Reference behaviour being reproduced (package/MDAnalysis/lib/nsgrid.pyx):
+//   _prepare_box :294-387  grid geometry        -> grid_geometry_reference()
+//   _pack_grid   :389-419  wrap + cell of atom  -> cell_key_kernel, counting sort
+//   search       :499-580  27-cell stencil      -> pair_search_kernel<.., SELF=false>
+//   self_search  :582-644  in-cell + 13 cells   -> pair_search_kernel<.., SELF=true>
+//   calc_distsq  :483-497  float32 diff, double minimum image, d2 <= cutoff^2
+//
+// B200 design: instead of the reference's linked list (head_id/next_id) the
+// atoms are counting-sorted by cell key (key = frame*ncell + cell) so that a
+// cell is one contiguous run of float4 {x,y,z,index}; one thread owns one query
+// (queries are processed in cell-sorted order, so the lanes of a warp read the
+// same candidate runs and the 16-byte loads are L1 broadcasts).  Each candidate
+// is first rejected in FP32 against a threshold widened by a rigorous error
+// band; survivors are re-evaluated with the reference's exact float32->float64
+// arithmetic (geom.cuh) and only that exact d2 takes the decision, which is
+// what makes pair sets and histogram counts bit-identical.
+#pragma once
+#include "common.cuh"
+
+namespace mdagpu {
+
+// ---- geometry --------------------------------------------------------------------
+// The reference's own grid (needed for parity on triclinic boxes, where its
+// 27-cell stencil is not always complete).
+void grid_geometry_reference(double cutoff, const float *box6, const float *h9, int pbc,
+                             GridGeom *g, float *max_cutoff);
+// Any complete orthorhombic grid with cells >= cutoff (used where the result is
+// independent of the grid: orthorhombic / no-box searches).
+void grid_geometry_ortho_free(double cutoff, const float *L3, const double *origin, int pbc,
+                              GridGeom *g);
+// a single cell holding everything (all-pairs / brute force)
+void grid_geometry_single(GridGeom *g);
+
+// Per frame-set description living in device memory (one entry per frame, or a
+// single entry shared by all frames).
+struct FrameGeom {
+    GridGeom grid;
+    BoxParams box;
+    int64_t cell_base;     // offset of this frame's cells in the flattened key space
+};
+
+// ---- cell keys + counting sort -------------------------------------------------------
+// keys[f*n + i] = cell_base[f] + cell(i); counts[key]++ .
+// wrap: 0 = coordinates used as given; 1 = wrapped into the cell first (binned and
+// stored wrapped, FastNS); 2 = binned by the wrapped position but stored as
+// given (lib.distances ortho flavour works on unwrapped input).
+__global__ void cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
+                                const FrameGeom *__restrict__ fg, int per_frame, int wrap,
+                                uint32_t *__restrict__ keys, uint32_t *__restrict__ counts);
+// exclusive scan of counts[0..n) into starts[0..n], starts[n] = total (single CTA, chunked)
+__global__ void exclusive_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ starts,
+                                      uint64_t n);
+// sorted[starts[key] + slot] = {x,y,z,i}; cursor must be zeroed; wraps like cell_key_kernel
+__global__ void cell_scatter_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
+                                    const FrameGeom *__restrict__ fg, int per_frame, int wrap,
+                                    const uint32_t *__restrict__ keys,
+                                    const uint32_t *__restrict__ starts,
+                                    uint32_t *__restrict__ cursor, float4 *__restrict__ sorted,
+                                    uint32_t *__restrict__ sorted_key);
+
+struct CellList {
+    DevBuf keys, counts, starts, cursor, sorted, sorted_key;
+    uint64_t n = 0, nframes = 0, total_cells = 0;
+    const float4 *atoms() const { return sorted.as<float4>(); }
+    const uint32_t *start() const { return starts.as<uint32_t>(); }
+    const uint32_t *key_of_sorted() const { return sorted_key.as<uint32_t>(); }
+};
+
+// Builds the sorted cell list of `xyz` [nframes, n, 3] (device pointer).
+int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameGeom *fg_dev,
+                    int per_frame, uint64_t total_cells, int wrap, cudaStream_t st, CellList *out);
+
+// ---- FP32 pre-filter ----------------------------------------------------------------
+// Returns an FP32 estimate of the minimum-image d2 whose relative error is far
+// below the 1e-5 band the callers put on their thresholds.
+template <int MIC>
+__device__ __forceinline__ float pair_d2_filter(float tx, float ty, float tz, const BoxParams &b)
+{
+    if (MIC == MIC_ORTHO_LAZY) {
+        tx = tx > b.half[0] ? tx - b.L[0] : (tx <= -b.half[0] ? tx + b.L[0] : tx);
+        ty = ty > b.half[1] ? ty - b.L[1] : (ty <= -b.half[1] ? ty + b.L[1] : ty);
+        tz = tz > b.half[2] ? tz - b.L[2] : (tz <= -b.half[2] ? tz + b.L[2] : tz);
+        return fmaf(tx, tx, fmaf(ty, ty, tz * tz));
+    } else if (MIC == MIC_TRICLINIC) {
+        float best = FLT_MAX;
+#pragma unroll
+        for (int a = -1; a <= 1; ++a) {
+            float xa = tx + b.h[0] * (float)a;
+#pragma unroll
+            for (int bb = -1; bb <= 1; ++bb) {
+                float xab = xa + b.h[3] * (float)bb;
+                float yb = ty + b.h[4] * (float)bb;
+#pragma unroll
+                for (int c = -1; c <= 1; ++c) {
+                    float x = xab + b.h[6] * (float)c;
+                    float y = yb + b.h[7] * (float)c;
+                    float z = tz + b.h[8] * (float)c;
+                    best = fminf(best, fmaf(x, x, fmaf(y, y, z * z)));
+                }
+            }
+        }
+        return best;
+    } else {
+        return fmaf(tx, tx, fmaf(ty, ty, tz * tz));
+    }
+}
+
+// half-shell route of self_search (nsgrid.pyx:603-605), slot 0 = home cell;
+// packed as (dx+1) | (dy+1)<<2 | (dz+1)<<4
+__device__ __constant__ static const unsigned kSelfRoute[14] = { 21u, 22u, 26u, 25u, 24u, 6u, 10u,
+                                                                 9u, 8u, 38u, 42u, 41u, 40u, 37u };
+
+// Thresholds for the FP32 pre-filter.  `d_abs_err` is an absolute error bound on
+// the FP32 distance estimate on top of its ~1e-6 relative error: zero except for
+// the triclinic image sums, whose intermediate values are box-sized.
+static inline double tric_abs_err(const float *h9)
+{
+    double s = 0.0;
+    for (int k = 0; k < 9; ++k) s += fabs((double)h9[k]);
+    return 2e-6 * s;
+}
+static inline float filter_threshold(double d2_max, double d_abs_err)
+{
+    double c = sqrt(d2_max > 0.0 ? d2_max : 0.0) + d_abs_err;
+    double t = c * c * (1.0 + 1e-5) + 1e-30;
+    float f = (float)t;
+    if ((double)f < t) f = nextafterf(f, INFINITY);
+    return f;
+}
+// below this FP32 value a pair is certainly inside d2_max
+static inline float certain_threshold(double d2_max, double d_abs_err)
+{
+    double c = sqrt(d2_max > 0.0 ? d2_max : 0.0) - d_abs_err;
+    if (c <= 0.0) return 0.0f;
+    double t = c * c * (1.0 - 1e-5);
+    float f = (float)t;
+    if ((double)f >= t) f = nextafterf(f, 0.0f);
+    return f;
+}
+
+// ---- traversal ---------------------------------------------------------------------
+struct SearchParams {
+    double d2_max;       // keep d2 <= d2_max (exact, double)
+    double d2_min;       // and d2 > d2_min (set to -1 to disable)
+    float d2_filter;     // FP32 rejection threshold (>= d2_max * (1 + band))
+    int use_filter;      // 0 for flavours without a safe FP32 bound
+    int stencil;         // 1: 27/13-cell stencil; 0: single cell (all pairs)
+};
+
+// One thread per query, in cell-sorted order.  `Sink` receives every accepted
+// pair: sink.hit(query_index, candidate_index, d2, frame).
+//   SELF = false : queries `q` (sorted list QL) against candidates CL, 27 cells
+//   SELF = true  : QL == CL; in-cell pairs with a later slot + 13-cell half shell
+template <int MIC, bool SELF, class Sink>
+__global__ void __launch_bounds__(Sink::THREADS)
+pair_search_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_keys,
+                   uint64_t nq_per_frame, const float4 *__restrict__ c_atoms,
+                   const uint32_t *__restrict__ c_start, const FrameGeom *__restrict__ fgs,
+                   int per_frame, SearchParams sp, Sink sink)
+{
+    __shared__ FrameGeom sfg;
+    const uint64_t f = blockIdx.y;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(fgs + (per_frame ? f : 0));
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sfg);
+        for (int w = threadIdx.x; w < (int)(sizeof(FrameGeom) / 4); w += blockDim.x) dst[w] = src[w];
+    }
+    sink.begin();
+    __syncthreads();
+    const FrameGeom &fg = sfg;
+    const BoxParams box = sfg.box;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nq_per_frame) {
+        const float4 q = q_atoms[f * nq_per_frame + t];
+        const int qi = __float_as_int(q.w);
+        const int64_t base = per_frame ? fg.cell_base : (int64_t)f * fg.grid.ncell_total;
+        int cx = 0, cy = 0, cz = 0;
+        if (sp.stencil) {
+            int64_t cell = (int64_t)q_keys[f * nq_per_frame + t] - base;
+            cx = (int)(cell % fg.grid.ncells[0]);
+            int64_t r = cell / fg.grid.ncells[0];
+            cy = (int)(r % fg.grid.ncells[1]);
+            cz = (int)(r / fg.grid.ncells[1]);
+        }
+        // SELF: slot 0 is the home cell (later atoms only), then the 13-cell half
+        // shell in the reference's route order (nsgrid.pyx:603-605).
+        const int nsten = sp.stencil ? (SELF ? 14 : 27) : 1;
+        for (int s = 0; s < nsten; ++s) {
+            int64_t cell;
+            if (!sp.stencil) {
+                cell = 0;
+            } else if (SELF) {
+                unsigned r = kSelfRoute[s];
+                cell = cell_neighbor(fg.grid, cx + (int)(r & 3u) - 1, cy + (int)((r >> 2) & 3u) - 1,
+                                     cz + (int)((r >> 4) & 3u) - 1);
+            } else {
+                cell = cell_neighbor(fg.grid, cx + s / 9 - 1, cy + (s / 3) % 3 - 1, cz + s % 3 - 1);
+            }
+            if (cell < 0) continue;
+            uint32_t j0 = c_start[base + cell], j1 = c_start[base + cell + 1];
+            if (SELF && s == 0) j0 = (uint32_t)(f * nq_per_frame + t) + 1;   // later slots of the home cell
+            for (uint32_t j = j0; j < j1; ++j) {
+                const float4 c = c_atoms[j];
+                const float tx = q.x - c.x, ty = q.y - c.y, tz = q.z - c.z;   // a - b (nsgrid.pyx:486-488)
+                if (sp.use_filter) {
+                    float d2f = pair_d2_filter<MIC>(tx, ty, tz, box);
+                    if (d2f > sp.d2_filter) continue;
+                    if (Sink::FAST && sink.try_fast(qi, __float_as_int(c.w), d2f)) continue;
+                }
+                const double d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, c.x, c.y, c.z, box);
+                if (d2 <= sp.d2_max && d2 > sp.d2_min) sink.hit(qi, __float_as_int(c.w), d2, f);
+            }
+        }
+    }
+    sink.end();
+}
+
+// ---- sinks -----------------------------------------------------------------------------
+// Appends (i, j, sqrt(d2)) with one atomic per converged group of lanes.
+struct PairSink {
+    static constexpr int THREADS = 128;
+    long long *pairs;                 // [capacity][2]
+    double *dist;                     // [capacity]
+    unsigned long long *counter;      // total hits (keeps counting past capacity)
+    unsigned long long capacity;
+    int orient;                       // 1: emit (min(i,j), max(i,j))  (brute-force self variant)
+    static constexpr bool FAST = false;
+    __device__ __forceinline__ bool try_fast(int, int, float) { return false; }
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ void end() {}
+    __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t)
+    {
+        const unsigned m = __activemask();
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+        if (slot < capacity) {
+            longlong2 p;
+            p.x = i; p.y = j;
+            if (orient && i > j) { p.x = j; p.y = i; }
+            *reinterpret_cast<longlong2 *>(pairs + 2 * slot) = p;
+            dist[slot] = sqrt(d2);
+        }
+    }
+};
+
+}  // namespace mdagpu

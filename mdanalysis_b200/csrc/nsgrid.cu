@@ -1,0 +1,520 @@
+// nsgrid.cu -- FastNS on the GPU: grid geometry, counting-sort cell list, cutoff
+// pair search with warp-aggregated compaction, brute-force capped distances.
+// Reference: package/MDAnalysis/lib/nsgrid.pyx (cited per function) and
+// package/MDAnalysis/lib/distances.py:589-673, 1050-1130 (brute force).
+#include "engine.cuh"
+
+#include <math.h>
+#include <new>
+
+namespace mdagpu {
+
+// ---------------------------------------------------------------------------
+// host: grid geometry
+// ---------------------------------------------------------------------------
+static float sin_deg_f32(float deg)
+{
+    // nsgrid.pyx:119-122: float32 angle in radians, libm double sine, float32 result
+    deg = (float)((double)deg * (M_PI / 180.));
+    return (float)sin((double)deg);
+}
+
+void grid_geometry_reference(double cutoff_in, const float *box6, const float *h9, int pbc,
+                             GridGeom *g, float *max_cutoff)
+{
+    // nsgrid.pyx:294-387
+    float cutoff = (float)(cutoff_in > 1.0 ? cutoff_in : 1.0);
+    g->triclinic = (h9[3] != 0.0f || h9[6] != 0.0f || h9[7] != 0.0f);
+    g->pbc = pbc;
+    const float sa = sin_deg_f32(box6[3]), sb = sin_deg_f32(box6[4]), sg = sin_deg_f32(box6[5]);
+    float mc = h9[4] * sa;
+    mc = fminf(mc, h9[8] * sa);
+    mc = fminf(mc, h9[0] * sb);
+    mc = fminf(mc, h9[8] * sb);
+    mc = fminf(mc, h9[0] * sg);
+    mc = fminf(mc, h9[4] * sg);
+    mc /= 2;
+    if (max_cutoff) *max_cutoff = mc;
+
+    float min_cell = cutoff;
+    if (g->triclinic) {
+        const float s[3] = { sa, sb, sg };
+        for (int k = 0; k < 3; ++k) {
+            float c = cutoff / s[k];
+            if (c > min_cell) min_cell = c;
+        }
+    }
+    min_cell = (float)((double)min_cell + 0.001);
+    const float edge[3] = { h9[0], h9[4], h9[8] };
+    for (int k = 0; k < 3; ++k) {
+        double nc = floor((double)(edge[k] / min_cell));
+        g->ncells[k] = (int)(nc < 1290.0 ? nc : 1290.0);
+        if (pbc) {
+            if (g->ncells[k] <= 3) { g->ncells[k] = 1; g->periodic[k] = 0; }
+            else g->periodic[k] = 1;
+        } else {
+            if (g->ncells[k] <= 2) g->ncells[k] = 1;
+            g->periodic[k] = 0;
+        }
+    }
+    for (int k = 0; k < 9; ++k) g->cs[k] = 0.0;
+    g->origin[0] = g->origin[1] = g->origin[2] = 0.0;
+    g->cs[0] = (double)h9[0] / (double)g->ncells[0];
+    g->cs[3] = (double)(h9[3] / h9[4]);
+    g->cs[4] = (double)h9[4] / (double)g->ncells[1];
+    g->cs[6] = (double)(h9[6] / h9[8]);
+    g->cs[7] = (double)(h9[7] / h9[8]);
+    g->cs[8] = (double)h9[8] / (double)g->ncells[2];
+    g->ncell_total = (int64_t)g->ncells[0] * g->ncells[1] * g->ncells[2];
+}
+
+void grid_geometry_single(GridGeom *g)
+{
+    for (int k = 0; k < 3; ++k) { g->ncells[k] = 1; g->periodic[k] = 0; }
+    for (int k = 0; k < 9; ++k) g->cs[k] = 0.0;
+    g->origin[0] = g->origin[1] = g->origin[2] = 0.0;
+    g->cs[0] = g->cs[4] = g->cs[8] = INFINITY;   // every coordinate maps to cell 0
+    g->triclinic = 0;
+    g->pbc = 0;
+    g->ncell_total = 1;
+}
+
+// ---------------------------------------------------------------------------
+// device: cell keys, scan, scatter
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
+                const FrameGeom *__restrict__ fgs, int per_frame, int wrap,
+                uint32_t *__restrict__ keys, uint32_t *__restrict__ counts)
+{
+    const uint64_t total = n * nframes;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        const uint64_t f = t / n;
+        const FrameGeom &fg = fgs[per_frame ? f : 0];
+        float x = xyz[3 * t], y = xyz[3 * t + 1], z = xyz[3 * t + 2];
+        if (wrap) wrap_any(x, y, z, fg.box);
+        int64_t cell = 0;
+        if (fg.grid.ncell_total > 1) {
+            int c[3];
+            cell_of(fg.grid, x, y, z, c);
+            // the reference's C remainder can only leave [0,ncells) for positions
+            // outside the cell; clamp so that a bad input cannot corrupt memory
+            for (int k = 0; k < 3; ++k) c[k] = c[k] < 0 ? 0 : c[k];
+            cell = cell_linear(fg.grid, c);
+        }
+        const int64_t base = per_frame ? fg.cell_base : (int64_t)f * fg.grid.ncell_total;
+        const uint32_t key = (uint32_t)(base + cell);
+        keys[t] = key;
+        atomicAdd(&counts[key], 1u);
+    }
+}
+
+// single CTA, 1024 threads, chunked with a running carry
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ starts, uint64_t n)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? counts[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += u;
+            }
+            warp_sums[lane] = wi - w;   // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint32_t c = carry;
+        const uint32_t excl = c + warp_sums[warp] + incl - v;
+        if (i < n) starts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) starts[n] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+cell_scatter_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
+                    const FrameGeom *__restrict__ fgs, int per_frame, int wrap,
+                    const uint32_t *__restrict__ keys, const uint32_t *__restrict__ starts,
+                    uint32_t *__restrict__ cursor, float4 *__restrict__ sorted,
+                    uint32_t *__restrict__ sorted_key)
+{
+    const uint64_t total = n * nframes;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        const uint64_t f = t / n;
+        const FrameGeom &fg = fgs[per_frame ? f : 0];
+        float x = xyz[3 * t], y = xyz[3 * t + 1], z = xyz[3 * t + 2];
+        if (wrap == 1) wrap_any(x, y, z, fg.box);   // wrap == 2: binned wrapped, stored as given
+        const uint32_t key = keys[t];
+        const uint32_t slot = starts[key] + atomicAdd(&cursor[key], 1u);
+        sorted[slot] = make_float4(x, y, z, __int_as_float((int)(t - f * n)));
+        sorted_key[slot] = key;
+    }
+}
+
+int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameGeom *fg_dev,
+                    int per_frame, uint64_t total_cells, int wrap, cudaStream_t st, CellList *cl)
+{
+    const uint64_t total = n * nframes;
+    MDA_REQUIRE(total < 0xffffffffull && total_cells < 0xfffffff0ull,
+                "cell list too large for 32-bit keys (%llu atoms, %llu cells)",
+                (unsigned long long)total, (unsigned long long)total_cells);
+    cl->n = n; cl->nframes = nframes; cl->total_cells = total_cells;
+    MDA_CUDA(cl->keys.alloc(total * sizeof(uint32_t), st));
+    MDA_CUDA(cl->counts.alloc(total_cells * sizeof(uint32_t), st));
+    MDA_CUDA(cl->starts.alloc((total_cells + 1) * sizeof(uint32_t), st));
+    MDA_CUDA(cl->cursor.alloc(total_cells * sizeof(uint32_t), st));
+    MDA_CUDA(cl->sorted.alloc(total * sizeof(float4), st));
+    MDA_CUDA(cl->sorted_key.alloc(total * sizeof(uint32_t), st));
+    MDA_CUDA(cudaMemsetAsync(cl->counts.p, 0, total_cells * sizeof(uint32_t), st));
+    MDA_CUDA(cudaMemsetAsync(cl->cursor.p, 0, total_cells * sizeof(uint32_t), st));
+    if (total == 0) {
+        MDA_CUDA(cudaMemsetAsync(cl->starts.p, 0, (total_cells + 1) * sizeof(uint32_t), st));
+        return MDAGPU_OK;
+    }
+    unsigned grid = cdiv(total, 256);
+    const unsigned cap = (unsigned)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    MDA_LAUNCH(cell_key_kernel, grid, 256, 0, st, xyz, n, nframes, fg_dev, per_frame, wrap,
+               cl->keys.as<uint32_t>(), cl->counts.as<uint32_t>());
+    MDA_CHECK_LAUNCH();
+    MDA_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, st, cl->counts.as<uint32_t>(),
+               cl->starts.as<uint32_t>(), total_cells);
+    MDA_CHECK_LAUNCH();
+    MDA_LAUNCH(cell_scatter_kernel, grid, 256, 0, st, xyz, n, nframes, fg_dev, per_frame, wrap,
+               cl->keys.as<uint32_t>(), cl->starts.as<uint32_t>(), cl->cursor.as<uint32_t>(),
+               cl->sorted.as<float4>(), cl->sorted_key.as<uint32_t>());
+    MDA_CHECK_LAUNCH();
+    return MDAGPU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pair list container
+// ---------------------------------------------------------------------------
+}  // namespace mdagpu
+
+struct mdagpu_pairs {
+    long long *pairs = nullptr;     // device [count][2]
+    double *dist = nullptr;         // device [count]
+    unsigned long long count = 0, capacity = 0;
+    ~mdagpu_pairs()
+    {
+        if (pairs) cudaFree(pairs);
+        if (dist) cudaFree(dist);
+    }
+};
+
+struct mdagpu_grid {
+    mdagpu::FrameGeom fg;
+    mdagpu::FrameGeom *fg_dev = nullptr;
+    mdagpu::CellList cl;
+    double cutoff = 0.0;
+    float max_cutoff = 0.0f;
+    int mic = 0;
+    uint64_t n = 0;
+    ~mdagpu_grid()
+    {
+        if (fg_dev) cudaFree(fg_dev);
+    }
+};
+
+namespace mdagpu {
+
+template <int MIC, bool SELF>
+static int run_pair_search(const CellList &ql, uint64_t nq, const CellList &cl,
+                           const FrameGeom *fg_dev, const SearchParams &sp, uint64_t guess,
+                           int orient, cudaStream_t st, mdagpu_pairs *res)
+{
+    DevBuf counter;
+    MDA_CUDA(counter.alloc(sizeof(unsigned long long), st));
+    unsigned long long cap = guess < 1024 ? 1024 : guess;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (res->pairs) { cudaFree(res->pairs); res->pairs = nullptr; }
+        if (res->dist) { cudaFree(res->dist); res->dist = nullptr; }
+        MDA_CUDA(cudaMalloc(&res->pairs, cap * 2 * sizeof(long long)));
+        MDA_CUDA(cudaMalloc(&res->dist, cap * sizeof(double)));
+        res->capacity = cap;
+        MDA_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+        PairSink sink = { res->pairs, res->dist, counter.as<unsigned long long>(), cap, orient };
+        dim3 grid(cdiv(nq, PairSink::THREADS), 1);
+        MDA_LAUNCH_AS(SELF ? "pair_self_search" : "pair_search", (pair_search_kernel<MIC, SELF, PairSink>), grid, PairSink::THREADS, 0, st,
+                   ql.atoms(), ql.key_of_sorted(), nq, cl.atoms(), cl.start(), fg_dev, 0, sp, sink);
+        MDA_CHECK_LAUNCH();
+        unsigned long long found = 0;
+        MDA_CUDA(cudaMemcpyAsync(&found, counter.p, sizeof(found), cudaMemcpyDeviceToHost, st));
+        MDA_CUDA(cudaStreamSynchronize(st));
+        res->count = found;
+        if (found <= cap) return MDAGPU_OK;
+        cap = found;    // exact size known now: second pass cannot overflow
+    }
+    return set_error(MDAGPU_ERR_CUDA, "pair search overflowed twice");
+}
+
+template <bool SELF>
+static int dispatch_pair_search(int mic, const CellList &ql, uint64_t nq, const CellList &cl,
+                                const FrameGeom *fg_dev, const SearchParams &sp, uint64_t guess,
+                                int orient, cudaStream_t st, mdagpu_pairs *res)
+{
+    switch (mic) {
+    case MIC_NONE: return run_pair_search<MIC_NONE, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, st, res);
+    case MIC_ORTHO_ROUND: return run_pair_search<MIC_ORTHO_ROUND, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, st, res);
+    case MIC_ORTHO_LAZY: return run_pair_search<MIC_ORTHO_LAZY, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, st, res);
+    case MIC_TRICLINIC: return run_pair_search<MIC_TRICLINIC, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, st, res);
+    }
+    return set_error(MDAGPU_ERR_INVALID, "unknown minimum-image flavour %d", mic);
+}
+
+// expected number of hits per query from the mean density, for the first
+// allocation (overflow is handled by a second, exactly sized pass)
+static uint64_t guess_pairs(uint64_t nq, uint64_t nc, double cutoff, double volume)
+{
+    double per_query = nc;
+    if (volume > 0.0) {
+        double v = 4.0 / 3.0 * M_PI * cutoff * cutoff * cutoff / volume * (double)nc;
+        if (v < per_query) per_query = v;
+    }
+    double g = (double)nq * per_query * 1.25 + 4096.0;
+    if (g > 4.0e9) g = 4.0e9;
+    return (uint64_t)g;
+}
+
+}  // namespace mdagpu
+
+using namespace mdagpu;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" int mdagpu_grid_geometry(double cutoff, const float *box6, const float *h9, int pbc,
+                                    int *ncells3, double *cellsize9, int *periodic3,
+                                    int *triclinic, float *max_cutoff)
+{
+    MDA_REQUIRE(box6 && h9, "mdagpu_grid_geometry: box is NULL");
+    GridGeom g;
+    float mc = 0.0f;
+    grid_geometry_reference(cutoff, box6, h9, pbc, &g, &mc);
+    if (ncells3) memcpy(ncells3, g.ncells, sizeof g.ncells);
+    if (cellsize9) memcpy(cellsize9, g.cs, sizeof g.cs);
+    if (periodic3) memcpy(periodic3, g.periodic, sizeof g.periodic);
+    if (triclinic) *triclinic = g.triclinic;
+    if (max_cutoff) *max_cutoff = mc;
+    return MDAGPU_OK;
+}
+
+extern "C" int mdagpu_grid_create(double cutoff, const float *coords, uint64_t n, const float *box6,
+                                  const float *h9, int pbc, int space, mdagpu_stream_t stream,
+                                  mdagpu_grid **out)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    MDA_REQUIRE(out != nullptr, "mdagpu_grid_create: out is NULL");
+    *out = nullptr;
+    MDA_REQUIRE(box6 && h9, "mdagpu_grid_create: box is NULL");
+    // nsgrid.pyx:284-291
+    MDA_REQUIRE(!(box6[0] == 0.0f || box6[1] == 0.0f || box6[2] == 0.0f), "Any of the box dimensions cannot be 0");
+    MDA_REQUIRE(cutoff >= 0.0, "Cutoff must be positive");
+    mdagpu_grid *g = new (std::nothrow) mdagpu_grid;
+    if (!g) return set_error(MDAGPU_ERR_NOMEM, "out of host memory");
+    g->cutoff = cutoff;
+    g->n = n;
+    grid_geometry_reference(cutoff, box6, h9, pbc, &g->fg.grid, &g->max_cutoff);
+    if (cutoff > (double)g->max_cutoff) {
+        float mc = g->max_cutoff;
+        delete g;
+        return set_error(MDAGPU_ERR_INVALID, "Cutoff %g too large for box (max %g)", cutoff, (double)mc);
+    }
+    const int tri = g->fg.grid.triclinic;
+    // wrapping always happens (nsgrid.pyx:406-414); the minimum image only with pbc
+    g->fg.box = tri ? make_box_params(BOX_TRICLINIC, h9) : make_box_params(BOX_ORTHO, box6);
+    g->fg.cell_base = 0;
+    g->mic = pbc ? (tri ? MIC_TRICLINIC : MIC_ORTHO_LAZY) : MIC_NONE;
+    if (g->fg.grid.ncell_total > (int64_t)1 << 28) {
+        const long long nc = (long long)g->fg.grid.ncell_total;
+        delete g;
+        return set_error(MDAGPU_ERR_NOMEM, "grid of %lld cells is too large", nc);
+    }
+    cudaError_t e = cudaMalloc(&g->fg_dev, sizeof(FrameGeom));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->fg_dev, &g->fg, sizeof(FrameGeom), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { delete g; MDA_CUDA(e); }
+    StagedIn in;
+    e = in.init(coords, n * 3 * sizeof(float), space, st);
+    if (e != cudaSuccess) { delete g; MDA_CUDA(e); }
+    int rc = build_cell_list(in.as<float>(), n, 1, g->fg_dev, 0, (uint64_t)g->fg.grid.ncell_total, 1, st, &g->cl);
+    if (rc == MDAGPU_OK) {
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = set_error(MDAGPU_ERR_CUDA, "grid build failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != MDAGPU_OK) { delete g; return rc; }
+    *out = g;
+    return MDAGPU_OK;
+}
+
+extern "C" int mdagpu_grid_info(const mdagpu_grid *g, int *ncells3, double *cellsize9,
+                                int *periodic3, int *triclinic, float *max_cutoff)
+{
+    MDA_REQUIRE(g != nullptr, "mdagpu_grid_info: grid is NULL");
+    if (ncells3) memcpy(ncells3, g->fg.grid.ncells, sizeof g->fg.grid.ncells);
+    if (cellsize9) memcpy(cellsize9, g->fg.grid.cs, sizeof g->fg.grid.cs);
+    if (periodic3) memcpy(periodic3, g->fg.grid.periodic, sizeof g->fg.grid.periodic);
+    if (triclinic) *triclinic = g->fg.grid.triclinic;
+    if (max_cutoff) *max_cutoff = g->max_cutoff;
+    return MDAGPU_OK;
+}
+
+extern "C" void mdagpu_grid_free(mdagpu_grid *g) { delete g; }
+
+static double grid_volume(const mdagpu_grid *g)
+{
+    const GridGeom &gg = g->fg.grid;
+    return gg.cs[0] * gg.ncells[0] * gg.cs[4] * gg.ncells[1] * gg.cs[8] * gg.ncells[2];
+}
+
+extern "C" int mdagpu_grid_search(mdagpu_grid *g, const float *queries, uint64_t nq, int space,
+                                  mdagpu_stream_t stream, mdagpu_pairs **out)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    MDA_REQUIRE(g && out, "mdagpu_grid_search: NULL argument");
+    *out = nullptr;
+    mdagpu_pairs *res = new (std::nothrow) mdagpu_pairs;
+    if (!res) return set_error(MDAGPU_ERR_NOMEM, "out of host memory");
+    if (nq == 0 || g->n == 0) { *out = res; return MDAGPU_OK; }
+    StagedIn in;
+    cudaError_t e = in.init(queries, nq * 3 * sizeof(float), space, st);
+    if (e != cudaSuccess) { delete res; MDA_CUDA(e); }
+    CellList ql;   // queries are wrapped and binned exactly like grid atoms (nsgrid.pyx:551-560)
+    int rc = build_cell_list(in.as<float>(), nq, 1, g->fg_dev, 0, (uint64_t)g->fg.grid.ncell_total, 1, st, &ql);
+    if (rc == MDAGPU_OK) {
+        SearchParams sp;
+        sp.d2_max = g->cutoff * g->cutoff;   // nsgrid.pyx:540
+        sp.d2_min = -1.0;
+        sp.d2_filter = filter_threshold(sp.d2_max, g->mic == MIC_TRICLINIC ? tric_abs_err(g->fg.box.h) : 0.0);
+        sp.use_filter = 1;
+        sp.stencil = 1;
+        rc = dispatch_pair_search<false>(g->mic, ql, nq, g->cl, g->fg_dev, sp,
+                                         guess_pairs(nq, g->n, g->cutoff, grid_volume(g)), 0, st, res);
+    }
+    if (rc != MDAGPU_OK) { delete res; return rc; }
+    *out = res;
+    return MDAGPU_OK;
+}
+
+extern "C" int mdagpu_grid_self_search(mdagpu_grid *g, mdagpu_stream_t stream, mdagpu_pairs **out)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    MDA_REQUIRE(g && out, "mdagpu_grid_self_search: NULL argument");
+    *out = nullptr;
+    mdagpu_pairs *res = new (std::nothrow) mdagpu_pairs;
+    if (!res) return set_error(MDAGPU_ERR_NOMEM, "out of host memory");
+    if (g->n < 2) { *out = res; return MDAGPU_OK; }
+    SearchParams sp;
+    sp.d2_max = g->cutoff * g->cutoff;       // nsgrid.pyx:601
+    sp.d2_min = -1.0;
+    sp.d2_filter = filter_threshold(sp.d2_max, g->mic == MIC_TRICLINIC ? tric_abs_err(g->fg.box.h) : 0.0);
+    sp.use_filter = 1;
+    sp.stencil = 1;
+    int rc = dispatch_pair_search<true>(g->mic, g->cl, g->n, g->cl, g->fg_dev, sp,
+                                        guess_pairs(g->n, g->n, g->cutoff, grid_volume(g)) / 2 + 4096, 0, st, res);
+    if (rc != MDAGPU_OK) { delete res; return rc; }
+    *out = res;
+    return MDAGPU_OK;
+}
+
+extern "C" uint64_t mdagpu_pairs_count(const mdagpu_pairs *p) { return p ? p->count : 0; }
+
+extern "C" int mdagpu_pairs_export(const mdagpu_pairs *p, int64_t *pairs, double *distances,
+                                   int space, mdagpu_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    MDA_REQUIRE(p != nullptr, "mdagpu_pairs_export: NULL pairs");
+    if (p->count == 0) return MDAGPU_OK;
+    const cudaMemcpyKind kind = space == MDAGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (pairs) MDA_CUDA(cudaMemcpyAsync(pairs, p->pairs, p->count * 2 * sizeof(int64_t), kind, st));
+    if (distances) MDA_CUDA(cudaMemcpyAsync(distances, p->dist, p->count * sizeof(double), kind, st));
+    if (space != MDAGPU_DEVICE) MDA_CUDA(cudaStreamSynchronize(st));
+    return MDAGPU_OK;
+}
+
+extern "C" void mdagpu_pairs_free(mdagpu_pairs *p) { delete p; }
+
+// d <= max_cutoff on the rounded float64 distance  <=>  d2 <= largest double whose
+// correctly rounded sqrt is <= max_cutoff (sqrt is monotone).
+static double d2_threshold_le(double c)
+{
+    if (!(c >= 0.0)) return -1.0;
+    if (isinf(c)) return c;
+    double x = c * c;
+    while (sqrt(x) > c) x = nextafter(x, -INFINITY);
+    while (sqrt(nextafter(x, INFINITY)) <= c) x = nextafter(x, INFINITY);
+    return x;
+}
+
+extern "C" int mdagpu_capped_bruteforce(const float *ref, uint64_t n, const float *conf, uint64_t m,
+                                        double max_cutoff, double min_cutoff, int box_mode,
+                                        const float *box, int space, mdagpu_stream_t stream,
+                                        mdagpu_pairs **out)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    MDA_REQUIRE(out != nullptr, "mdagpu_capped_bruteforce: out is NULL");
+    *out = nullptr;
+    MDA_REQUIRE(box_mode >= 0 && box_mode <= 2, "bad box_mode %d", box_mode);
+    MDA_REQUIRE(box_mode == BOX_NONE || box != nullptr, "box is NULL");
+    const bool self = conf == nullptr;
+    mdagpu_pairs *res = new (std::nothrow) mdagpu_pairs;
+    if (!res) return set_error(MDAGPU_ERR_NOMEM, "out of host memory");
+    if (n == 0 || (!self && m == 0) || (self && n < 2)) { *out = res; return MDAGPU_OK; }
+
+    FrameGeom fg;
+    grid_geometry_single(&fg.grid);
+    fg.box = make_box_params(box_mode, box);
+    fg.cell_base = 0;
+    DevBuf fg_dev;
+    cudaError_t e = fg_dev.alloc(sizeof(FrameGeom), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fg_dev.p, &fg, sizeof(FrameGeom), cudaMemcpyHostToDevice, st);
+    StagedIn r, c;
+    if (e == cudaSuccess) e = r.init(ref, n * 3 * sizeof(float), space, st);
+    if (e == cudaSuccess && !self) e = c.init(conf, m * 3 * sizeof(float), space, st);
+    if (e != cudaSuccess) { delete res; MDA_CUDA(e); }
+    // the triclinic distance kernels work on wrapped copies (calc_distances.h:429-430);
+    // every atom carries its original index, so the slot order does not matter.
+    const int wrap = box_mode == BOX_TRICLINIC;
+    CellList rl, cl;
+    int rc = build_cell_list(r.as<float>(), n, 1, fg_dev.as<FrameGeom>(), 0, 1, wrap, st, &rl);
+    if (rc == MDAGPU_OK && !self)
+        rc = build_cell_list(c.as<float>(), m, 1, fg_dev.as<FrameGeom>(), 0, 1, wrap, st, &cl);
+    if (rc == MDAGPU_OK) {
+        SearchParams sp;
+        sp.d2_max = d2_threshold_le(max_cutoff);
+        sp.d2_min = min_cutoff >= 0.0 ? d2_threshold_le(min_cutoff) : -1.0;
+        sp.d2_filter = filter_threshold(sp.d2_max, box_mode == BOX_TRICLINIC ? tric_abs_err(fg.box.h) : 0.0);
+        sp.use_filter = box_mode != BOX_ORTHO;   // no safe FP32 bound for unwrapped ortho input
+        sp.stencil = 0;
+        const int mic = box_mode == BOX_ORTHO ? MIC_ORTHO_ROUND : (box_mode == BOX_TRICLINIC ? MIC_TRICLINIC : MIC_NONE);
+        const uint64_t guess = (self ? n * 32 : n * 64) + 4096;
+        if (self) rc = dispatch_pair_search<true>(mic, rl, n, rl, fg_dev.as<FrameGeom>(), sp, guess, 1, st, res);
+        else rc = dispatch_pair_search<false>(mic, rl, n, cl, fg_dev.as<FrameGeom>(), sp, guess, 0, st, res);
+    }
+    if (rc != MDAGPU_OK) { delete res; return rc; }
+    *out = res;
+    return MDAGPU_OK;
+}

@@ -1,0 +1,448 @@
+// rdf.cu -- InterRDF pair histogram (K9) and fused contacts (K2c) on top of the
+// pair engine.
+// Reference: package/MDAnalysis/analysis/rdf.py:268-291 (capped_distance +
+// np.histogram per frame), analysis/contacts.py:315-338 and
+// analysis/distances.py:102-108 (contact predicate d <= radius).
+//
+// Histogram design: every thread owns a private column of 16-bit counters in
+// shared memory (two bins per 32-bit word, word index = bin/2 * THREADS + tid,
+// so a warp always touches 32 distinct banks and no atomics are needed); a
+// counter that is about to wrap is flushed to the global 64-bit bin with one
+// atomic.  At the end of the CTA the columns are summed with a skewed,
+// conflict-free walk and merged into the global histogram with one 64-bit
+// atomic per non-empty bin.
+#include "engine.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace mdagpu {
+
+void grid_geometry_ortho_free(double cutoff, const float *L3, const double *origin, int pbc,
+                              GridGeom *g)
+{
+    const double cs_min = cutoff * (1.0 + 1e-4) + 1e-3;
+    g->triclinic = 0;
+    g->pbc = pbc;
+    for (int k = 0; k < 9; ++k) g->cs[k] = 0.0;
+    int64_t total = 1;
+    for (int k = 0; k < 3; ++k) {
+        g->origin[k] = origin ? origin[k] : 0.0;
+        double nc = floor((double)L3[k] / cs_min);
+        if (!(nc >= 1.0)) nc = 1.0;
+        if (nc > 256.0) nc = 256.0;              // keeps the key space small; cells only get larger
+        int n = (int)nc;
+        if (pbc) {
+            if (n < 3) { n = 1; g->periodic[k] = 0; }
+            else g->periodic[k] = 1;
+        } else {
+            g->periodic[k] = 0;
+        }
+        g->ncells[k] = n;
+        g->cs[4 * k] = (double)L3[k] / (double)n;
+        total *= n;
+    }
+    g->ncell_total = total;
+}
+
+// ---------------------------------------------------------------------------
+// histogram sink
+// ---------------------------------------------------------------------------
+template <int T>
+struct HistSink {
+    static constexpr int THREADS = T;
+    static constexpr bool FAST = true;
+    const double *thr;            // [nbins+1] exact thresholds on d2 (device)
+    unsigned long long *counts;   // [nbins] global histogram
+    int nbins, excl_a, excl_b;
+    float lo, inv_dr, band, d2_fast_max;
+
+    __device__ __forceinline__ uint32_t *column() const
+    {
+        extern __shared__ uint32_t s_hist[];
+        return s_hist + threadIdx.x;
+    }
+    __device__ __forceinline__ void begin()
+    {
+        extern __shared__ uint32_t s_hist[];
+        const int nwords = (nbins + 1) >> 1;
+        for (int w = threadIdx.x; w < nwords * T; w += T) s_hist[w] = 0u;
+    }
+    __device__ __forceinline__ void add(int k)
+    {
+        uint32_t *w = column() + (k >> 1) * T;
+        const uint32_t sh = (uint32_t)(k & 1) << 4;
+        uint32_t v = *w;
+        if (((v >> sh) & 0xffffu) == 0xffffu) {
+            atomicAdd(&counts[k], 65536ull);    // 65535 stored + this one
+            v &= ~(0xffffu << sh);
+        } else {
+            v += 1u << sh;
+        }
+        *w = v;
+    }
+    __device__ __forceinline__ bool excluded(int i, int j) const
+    {
+        return excl_a > 0 && (i / excl_a) == (j / excl_b);   // rdf.py:274-278
+    }
+    // FP32 binning: accepted only when the estimate is safely inside a bin and
+    // safely inside the cutoff; everything near a decision boundary goes to hit().
+    __device__ __forceinline__ bool try_fast(int i, int j, float d2f)
+    {
+        if (!(d2f < d2_fast_max)) return false;
+        const float u = (sqrtf(d2f) - lo) * inv_dr;
+        const float fk = floorf(u);
+        const float frac = u - fk;
+        if (!(frac > band && frac < 1.0f - band) || !(u > 0.0f) || !(fk < (float)nbins)) return false;
+        if (!excluded(i, j)) add((int)fk);
+        return true;
+    }
+    __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t)
+    {
+        if (excluded(i, j)) return;
+        if (!(d2 >= thr[0]) || !(d2 <= thr[nbins])) return;     // np.histogram keeps lo <= d <= hi
+        int k = (int)((sqrtf((float)d2) - lo) * inv_dr);
+        k = k < 0 ? 0 : (k > nbins - 1 ? nbins - 1 : k);
+        while (k > 0 && d2 < thr[k]) --k;
+        while (k < nbins - 1 && d2 >= thr[k + 1]) ++k;
+        add(k);
+    }
+    __device__ __forceinline__ void end()
+    {
+        extern __shared__ uint32_t s_hist[];
+        __syncthreads();
+        for (int k = threadIdx.x; k < nbins; k += T) {
+            const uint32_t *row = s_hist + (k >> 1) * T;
+            const uint32_t sh = (uint32_t)(k & 1) << 4;
+            unsigned long long sum = 0;
+            for (int u = 0; u < T; ++u) sum += (row[(u + threadIdx.x) & (T - 1)] >> sh) & 0xffffu;
+            if (sum) atomicAdd(&counts[k], sum);
+        }
+    }
+};
+
+// fallback for very many bins: straight global atomics
+struct HistSinkGlobal {
+    static constexpr int THREADS = 128;
+    static constexpr bool FAST = false;
+    const double *thr;
+    unsigned long long *counts;
+    int nbins, excl_a, excl_b;
+    float lo, inv_dr, band, d2_fast_max;
+    __device__ __forceinline__ bool try_fast(int, int, float) { return false; }
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ void end() {}
+    __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t)
+    {
+        if (excl_a > 0 && (i / excl_a) == (j / excl_b)) return;
+        if (!(d2 >= thr[0]) || !(d2 <= thr[nbins])) return;
+        int k = (int)((sqrtf((float)d2) - lo) * inv_dr);
+        k = k < 0 ? 0 : (k > nbins - 1 ? nbins - 1 : k);
+        while (k > 0 && d2 < thr[k]) --k;
+        while (k < nbins - 1 && d2 >= thr[k + 1]) ++k;
+        atomicAdd(&counts[k], 1ull);
+    }
+};
+
+// contacts: pair count per frame and optional per-atom degree
+struct CountSink {
+    static constexpr int THREADS = 128;
+    static constexpr bool FAST = false;
+    unsigned long long *counts;   // [nframes]
+    int *degree;                  // [nframes*n] or NULL
+    uint64_t n;
+    unsigned local;
+    __device__ __forceinline__ bool try_fast(int, int, float) { return false; }
+    __device__ __forceinline__ void begin() { local = 0; }
+    __device__ __forceinline__ void hit(int i, int j, double, uint64_t f)
+    {
+        ++local;
+        if (degree) {
+            atomicAdd(&degree[f * n + i], 1);
+            atomicAdd(&degree[f * n + j], 1);
+        }
+    }
+    __device__ __forceinline__ void end()
+    {
+        unsigned v = local;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counts[blockIdx.y], (unsigned long long)v);
+    }
+};
+
+template <int MIC, class Sink>
+static int launch_hist(const CellList &ql, uint64_t nq, const CellList &cl, const FrameGeom *fg_dev,
+                       int per_frame, uint64_t nframes, const SearchParams &sp, const Sink &sink,
+                       size_t smem, cudaStream_t st)
+{
+    auto kern = pair_search_kernel<MIC, false, Sink>;
+    if (smem > 48 * 1024)
+        MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(nq, Sink::THREADS), (unsigned)nframes);
+    MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, smem, st, ql.atoms(), ql.key_of_sorted(), nq,
+                  cl.atoms(), cl.start(), fg_dev, per_frame, sp, sink);
+    MDA_CHECK_LAUNCH();
+    return MDAGPU_OK;
+}
+
+template <class Sink>
+static int dispatch_hist(int mic, const CellList &ql, uint64_t nq, const CellList &cl,
+                         const FrameGeom *fg_dev, int per_frame, uint64_t nframes,
+                         const SearchParams &sp, const Sink &sink, size_t smem, cudaStream_t st)
+{
+    switch (mic) {
+    case MIC_NONE: return launch_hist<MIC_NONE>(ql, nq, cl, fg_dev, per_frame, nframes, sp, sink, smem, st);
+    case MIC_ORTHO_ROUND: return launch_hist<MIC_ORTHO_ROUND>(ql, nq, cl, fg_dev, per_frame, nframes, sp, sink, smem, st);
+    case MIC_ORTHO_LAZY: return launch_hist<MIC_ORTHO_LAZY>(ql, nq, cl, fg_dev, per_frame, nframes, sp, sink, smem, st);
+    case MIC_TRICLINIC: return launch_hist<MIC_TRICLINIC>(ql, nq, cl, fg_dev, per_frame, nframes, sp, sink, smem, st);
+    }
+    return set_error(MDAGPU_ERR_INVALID, "unknown minimum-image flavour %d", mic);
+}
+
+// bounding box of [nframes, n, 3] coordinates (for no-box grids)
+__global__ void __launch_bounds__(256)
+bbox_kernel(const float *__restrict__ xyz, uint64_t total, float *__restrict__ lohi)
+{
+    float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (uint64_t)gridDim.x * blockDim.x)
+        for (int k = 0; k < 3; ++k) {
+            float v = xyz[3 * t + k];
+            lo[k] = fminf(lo[k], v);
+            hi[k] = fmaxf(hi[k], v);
+        }
+    for (int k = 0; k < 3; ++k) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            // ordered-int trick for float atomics (values are finite)
+            int l = __float_as_int(lo[k]), h = __float_as_int(hi[k]);
+            if (l >= 0) atomicMin((int *)&lohi[k], l); else atomicMax((unsigned *)&lohi[k], (unsigned)l);
+            if (h >= 0) atomicMax((int *)&lohi[3 + k], h); else atomicMin((unsigned *)&lohi[3 + k], (unsigned)h);
+        }
+    }
+}
+
+}  // namespace mdagpu
+
+using namespace mdagpu;
+
+extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B, uint64_t nb,
+                                     uint64_t nframes, const float *box6, const float *h9,
+                                     int boxes_per_frame, int mic, int wrap, double cutoff,
+                                     double d2_max, int use_grid, const double *thresholds,
+                                     int nbins, double r_lo, double r_hi, int excl_a, int excl_b,
+                                     unsigned long long *counts, int space, mdagpu_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    MDA_REQUIRE(A && thresholds && counts, "mdagpu_rdf_accumulate: NULL argument");
+    MDA_REQUIRE(nbins > 0, "mdagpu_rdf_accumulate: nbins must be positive");
+    MDA_REQUIRE(mic >= 0 && mic <= 3, "mdagpu_rdf_accumulate: bad mic %d", mic);
+    MDA_REQUIRE(mic == MIC_NONE || (box6 && h9), "mdagpu_rdf_accumulate: box is NULL");
+    MDA_REQUIRE((excl_a > 0) == (excl_b > 0), "mdagpu_rdf_accumulate: exclusion block needs two sizes");
+    const bool same = (B == nullptr || B == A);
+    if (same) nb = na;
+    if (nframes == 0 || na == 0 || nb == 0) return MDAGPU_OK;
+
+    // per-frame geometry on the host
+    const uint64_t nbox = boxes_per_frame ? nframes : 1;
+    std::vector<FrameGeom> fgs(nbox);
+    int64_t base = 0;
+    for (uint64_t f = 0; f < nbox; ++f) {
+        FrameGeom &fg = fgs[f];
+        const float *b6 = box6 ? box6 + 6 * f : nullptr;
+        const float *hh = h9 ? h9 + 9 * f : nullptr;
+        const bool tri = hh && (hh[3] != 0.0f || hh[6] != 0.0f || hh[7] != 0.0f);
+        if (use_grid) {
+            float mc = 0.0f;
+            grid_geometry_reference(cutoff, b6, hh, 1, &fg.grid, &mc);
+            // FastNS refuses such a cutoff (nsgrid.pyx:288-291)
+            MDA_REQUIRE(!(cutoff > (double)mc), "Cutoff %g too large for box (max %g)", cutoff, (double)mc);
+        } else {
+            grid_geometry_single(&fg.grid);
+        }
+        if (mic == MIC_NONE && !b6) fg.box = make_box_params(BOX_NONE, nullptr);
+        else fg.box = tri ? make_box_params(BOX_TRICLINIC, hh) : make_box_params(BOX_ORTHO, b6);
+        fg.cell_base = base;
+        base += fg.grid.ncell_total;
+    }
+    const int64_t cells_per_frame = boxes_per_frame ? 0 : fgs[0].grid.ncell_total;
+    double d_abs_err = 0.0;
+    if (mic == MIC_TRICLINIC)
+        for (uint64_t f = 0; f < nbox; ++f) d_abs_err = fmax(d_abs_err, tric_abs_err(fgs[f].box.h));
+
+    StagedIn a_in, b_in, thr_in;
+    StagedOut cnt;
+    MDA_CUDA(a_in.init(A, nframes * na * 3 * sizeof(float), space, st));
+    if (!same) MDA_CUDA(b_in.init(B, nframes * nb * 3 * sizeof(float), space, st));
+    MDA_CUDA(thr_in.init(thresholds, (size_t)(nbins + 1) * sizeof(double), MDAGPU_HOST, st));   // always a host array
+    MDA_CUDA(cnt.init(counts, (size_t)nbins * sizeof(unsigned long long), space, st, true));
+
+    SearchParams sp;
+    sp.d2_max = d2_max;
+    sp.d2_min = -1.0;
+    sp.d2_filter = filter_threshold(d2_max, d_abs_err);
+    sp.use_filter = mic != MIC_ORTHO_ROUND;
+    sp.stencil = use_grid ? 1 : 0;
+
+    const float lo = (float)r_lo;
+    const float inv_dr = (float)((double)nbins / (r_hi - r_lo));
+    // FP32 error of the bin coordinate u = (d - lo) * inv_dr: relative 1e-6 of d plus
+    // the absolute part; keep well clear of it (a band >= 0.5 disables the fast path)
+    const double u_err = (2e-6 * r_hi + 2.0 * d_abs_err) * (double)nbins / (r_hi - r_lo);
+    const float band = (float)fmax(2e-3, 10.0 * u_err);
+    const float d2_fast_max = certain_threshold(d2_max, d_abs_err);
+
+    // frames are processed in chunks that keep keys 32-bit and the grid within limits
+    uint64_t chunk = nframes;
+    const uint64_t per_frame_atoms = na > nb ? na : nb;
+    const uint64_t max_atoms = 1ull << 27;                 // 128 Mi atoms (2 GiB of float4) per chunk
+    if (chunk * per_frame_atoms > max_atoms) chunk = max_atoms / per_frame_atoms ? max_atoms / per_frame_atoms : 1;
+    if (chunk > 65535) chunk = 65535;
+    if (!boxes_per_frame && cells_per_frame > 0) {
+        uint64_t by_cells = (uint64_t)((1ull << 30) / (uint64_t)cells_per_frame);
+        if (by_cells < 1) by_cells = 1;
+        if (chunk > by_cells) chunk = by_cells;
+    }
+
+    DevBuf fg_dev;
+    for (uint64_t f0 = 0; f0 < nframes; f0 += chunk) {
+        const uint64_t fc = (nframes - f0 < chunk) ? nframes - f0 : chunk;
+        uint64_t total_cells;
+        if (boxes_per_frame) {
+            // re-base this chunk's cells at zero
+            std::vector<FrameGeom> part(fgs.begin() + f0, fgs.begin() + f0 + fc);
+            const int64_t b0 = part[0].cell_base;
+            for (auto &p : part) p.cell_base -= b0;
+            total_cells = (uint64_t)(part.back().cell_base + part.back().grid.ncell_total);
+            MDA_CUDA(fg_dev.alloc(fc * sizeof(FrameGeom), st));
+            MDA_CUDA(cudaMemcpyAsync(fg_dev.p, part.data(), fc * sizeof(FrameGeom), cudaMemcpyHostToDevice, st));
+            MDA_CUDA(cudaStreamSynchronize(st));   // `part` dies at the end of this scope
+        } else {
+            total_cells = (uint64_t)cells_per_frame * fc;
+            if (f0 == 0) {
+                MDA_CUDA(fg_dev.alloc(sizeof(FrameGeom), st));
+                MDA_CUDA(cudaMemcpyAsync(fg_dev.p, fgs.data(), sizeof(FrameGeom), cudaMemcpyHostToDevice, st));
+            }
+        }
+        const FrameGeom *fgd = fg_dev.as<FrameGeom>();
+        CellList cl, ql;
+        int rc = build_cell_list((same ? a_in.as<float>() : b_in.as<float>()) + f0 * nb * 3, nb, fc, fgd,
+                                 boxes_per_frame, total_cells, wrap, st, &cl);
+        if (rc) return rc;
+        if (!same) {
+            rc = build_cell_list(a_in.as<float>() + f0 * na * 3, na, fc, fgd, boxes_per_frame,
+                                 total_cells, wrap, st, &ql);
+            if (rc) return rc;
+        }
+        const CellList &qq = same ? cl : ql;
+        const int nwords = (nbins + 1) / 2;
+        if ((size_t)nwords * 256 * 4 <= 100 * 1024) {
+            HistSink<256> sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, lo, inv_dr, band, d2_fast_max };
+            rc = dispatch_hist(mic, qq, na, cl, fgd, boxes_per_frame, fc, sp, sink, (size_t)nwords * 256 * 4, st);
+        } else if ((size_t)nwords * 64 * 4 <= 200 * 1024) {
+            HistSink<64> sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, lo, inv_dr, band, d2_fast_max };
+            rc = dispatch_hist(mic, qq, na, cl, fgd, boxes_per_frame, fc, sp, sink, (size_t)nwords * 64 * 4, st);
+        } else {
+            HistSinkGlobal sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, lo, inv_dr, band, d2_fast_max };
+            rc = dispatch_hist(mic, qq, na, cl, fgd, boxes_per_frame, fc, sp, sink, 0, st);
+        }
+        if (rc) return rc;
+    }
+    MDA_CUDA(cnt.finish());
+    if (space == MDAGPU_HOST) MDA_CUDA(cudaStreamSynchronize(st));
+    return MDAGPU_OK;
+}
+
+extern "C" int mdagpu_contacts_self(const float *xyz, uint64_t n, uint64_t nframes, int box_mode,
+                                    const float *box, double d2_max, double cutoff,
+                                    unsigned long long *counts, int32_t *degree, int space,
+                                    mdagpu_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    MDA_REQUIRE(xyz && counts, "mdagpu_contacts_self: NULL argument");
+    MDA_REQUIRE(box_mode >= 0 && box_mode <= 2, "bad box_mode %d", box_mode);
+    MDA_REQUIRE(box_mode == BOX_NONE || box != nullptr, "box is NULL");
+    MDA_REQUIRE(nframes <= 65535, "mdagpu_contacts_self: at most 65535 frames per call");
+    if (nframes == 0) return MDAGPU_OK;
+
+    StagedIn in;
+    StagedOut cnt, deg;
+    MDA_CUDA(in.init(xyz, nframes * n * 3 * sizeof(float), space, st));
+    MDA_CUDA(cnt.init(counts, nframes * sizeof(unsigned long long), space, st));
+    MDA_CUDA(cudaMemsetAsync(cnt.dev, 0, nframes * sizeof(unsigned long long), st));
+    if (degree) {
+        MDA_CUDA(deg.init(degree, nframes * n * sizeof(int32_t), space, st));
+        MDA_CUDA(cudaMemsetAsync(deg.dev, 0, nframes * n * sizeof(int32_t), st));
+    }
+    if (n >= 2) {
+        FrameGeom fg;
+        fg.cell_base = 0;
+        fg.box = make_box_params(box_mode, box);
+        int mic = MIC_NONE, wrap = 0, stencil = 1;
+        if (box_mode == BOX_ORTHO) {
+            // lib.distances flavour on unwrapped input: bin by the wrapped position,
+            // evaluate on the coordinates as given
+            mic = MIC_ORTHO_ROUND; wrap = 2;
+            grid_geometry_ortho_free(cutoff, box, nullptr, 1, &fg.grid);
+        } else if (box_mode == BOX_TRICLINIC) {
+            mic = MIC_TRICLINIC; wrap = 1; stencil = 0;
+            grid_geometry_single(&fg.grid);
+        } else {
+            DevBuf lohi;
+            MDA_CUDA(lohi.alloc(6 * sizeof(float), st));
+            const float init[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
+            MDA_CUDA(cudaMemcpyAsync(lohi.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+            unsigned grid = cdiv(nframes * n, 256);
+            if (grid > (unsigned)num_sms() * 8) grid = (unsigned)num_sms() * 8;
+            MDA_LAUNCH(bbox_kernel, grid, 256, 0, st, in.as<float>(), nframes * n, lohi.as<float>());
+            MDA_CHECK_LAUNCH();
+            float h[6];
+            MDA_CUDA(cudaMemcpyAsync(h, lohi.p, sizeof h, cudaMemcpyDeviceToHost, st));
+            MDA_CUDA(cudaStreamSynchronize(st));
+            float L[3];
+            double origin[3];
+            for (int k = 0; k < 3; ++k) {
+                const double pad = 1e-3 + 1e-5 * fmax(fabs((double)h[k]), fabs((double)h[3 + k]));
+                origin[k] = (double)h[k] - pad;
+                L[k] = (float)((double)h[3 + k] - (double)h[k] + 2.0 * pad + cutoff * 1e-3);
+            }
+            grid_geometry_ortho_free(cutoff, L, origin, 0, &fg.grid);
+        }
+        DevBuf fg_dev;
+        MDA_CUDA(fg_dev.alloc(sizeof(FrameGeom), st));
+        MDA_CUDA(cudaMemcpyAsync(fg_dev.p, &fg, sizeof(FrameGeom), cudaMemcpyHostToDevice, st));
+        CellList cl;
+        int rc = build_cell_list(in.as<float>(), n, nframes, fg_dev.as<FrameGeom>(), 0,
+                                 (uint64_t)fg.grid.ncell_total * nframes, wrap, st, &cl);
+        if (rc) return rc;
+        SearchParams sp;
+        sp.d2_max = d2_max;
+        sp.d2_min = -1.0;
+        sp.d2_filter = filter_threshold(d2_max, mic == MIC_TRICLINIC ? tric_abs_err(fg.box.h) : 0.0);
+        sp.use_filter = mic != MIC_ORTHO_ROUND;
+        sp.stencil = stencil;
+        CountSink sink = { cnt.as<unsigned long long>(), degree ? deg.as<int>() : nullptr, n, 0u };
+        dim3 grid(cdiv(n, CountSink::THREADS), (unsigned)nframes);
+        const FrameGeom *fgd = fg_dev.as<FrameGeom>();
+        switch (mic) {
+        case MIC_NONE:
+            MDA_LAUNCH_AS("contacts_pair_count", (pair_search_kernel<MIC_NONE, true, CountSink>), grid, CountSink::THREADS, 0, st, cl.atoms(), cl.key_of_sorted(), n, cl.atoms(), cl.start(), fgd, 0, sp, sink);
+            break;
+        case MIC_ORTHO_ROUND:
+            MDA_LAUNCH_AS("contacts_pair_count", (pair_search_kernel<MIC_ORTHO_ROUND, true, CountSink>), grid, CountSink::THREADS, 0, st, cl.atoms(), cl.key_of_sorted(), n, cl.atoms(), cl.start(), fgd, 0, sp, sink);
+            break;
+        default:
+            MDA_LAUNCH_AS("contacts_pair_count", (pair_search_kernel<MIC_TRICLINIC, true, CountSink>), grid, CountSink::THREADS, 0, st, cl.atoms(), cl.key_of_sorted(), n, cl.atoms(), cl.start(), fgd, 0, sp, sink);
+            break;
+        }
+        MDA_CHECK_LAUNCH();
+        MDA_CUDA(cudaStreamSynchronize(st));   // scratch (cell list) is released on return
+    }
+    MDA_CUDA(cnt.finish());
+    if (degree) MDA_CUDA(deg.finish());
+    return MDAGPU_OK;
+}

@@ -1,0 +1,99 @@
+"""QCP RMSD / optimal rotation -- mirror of ``MDAnalysis/lib/qcprot.pyx``.
+
+``CalcRMSDRotationalMatrix(ref, conf, N, rot, weights)`` (qcprot.pyx:282-320)
+keeps its call signature: centred ``(N, 3)`` structures, ``rot`` a flat
+9-element array filled in place (or ``None``), ``weights`` ``(N,)`` or ``None``;
+returns the RMSD.  ``R = rot.reshape(3, 3)`` satisfies ``conf @ R ~ ref``.
+
+float32 inputs are accepted like in the reference; the GPU accumulates in
+float64 in both cases (the reference accumulates in the input precision and
+itself documents float32 errors of ~1e-3, rms.py:690-692), so float32 results
+agree with the reference's float32 ones to about 1e-4 relative and with its
+float64 ones to 1e-12.
+
+``qcp_trajectory`` is the batched twin driving ``RMSD`` / ``AlignTraj``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .._cabi import DEVICE, HOST, check, current_stream, is_tensor, load, ptr, tensor_ptr
+
+
+def CalcRMSDRotationalMatrix(ref, conf, N, rot, weights):
+    """RMSD after optimal superposition and (optionally) the rotation matrix."""
+    if ref is None or conf is None:
+        raise TypeError("Argument 'ref'/'conf' must not be None")
+    ref64 = np.ascontiguousarray(ref, dtype=np.float64)
+    conf64 = np.ascontiguousarray(conf, dtype=np.float64)
+    if ref64.ndim != 2 or conf64.ndim != 2:
+        raise ValueError("Buffer has wrong number of dimensions (expected 2)")
+    N = int(N)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    r = None if rot is None else np.zeros(9, dtype=np.float64)
+    val = C.c_double(0.0)
+    check(load().mdagpu_qcp(ptr(ref64), ptr(conf64), N, ptr(r), ptr(w), C.byref(val), HOST, None))
+    if rot is not None:
+        rot[:] = r
+    return float(val.value)
+
+
+def qcp_trajectory(traj, reference, select=None, weights=None, want_rotation=False,
+                   align=False, convention=0, allclose_shortcut=False, out=None):
+    """Per-frame centring + QCP for a whole trajectory block in one launch.
+
+    traj       float32 [F, natoms, 3] NumPy array or torch CUDA tensor
+    reference  float32 [nsel, 3] un-centred reference positions of the fitted atoms
+    select     int indices of the fitted atoms within a frame (None: all atoms)
+    weights    relative weights [nsel] (already divided by their mean) or None
+    align      also move every atom of every frame onto the reference
+               (``out`` = destination with traj's shape; ``out is traj`` = in place)
+    convention 0: RMSD (rot: mobile @ R ~ ref, rms.py:699-711)
+               1: AlignTraj (rot = rotation_matrix(mobile, ref), applied as x @ R.T)
+    Returns (rmsd [F], rot [F,3,3] or None, aligned or None) of the input kind.
+    """
+    dev = is_tensor(traj)
+    F, natoms = int(traj.shape[0]), int(traj.shape[1])
+    if tuple(traj.shape[2:]) != (3,):
+        raise ValueError(f"traj must have shape (F, n, 3), got {tuple(traj.shape)}")
+    sel = None if select is None else np.ascontiguousarray(select, dtype=np.int32)
+    nsel = natoms if sel is None else len(sel)
+    if sel is not None and nsel and (sel.min() < 0 or sel.max() >= natoms):
+        raise IndexError("selection index out of range")
+    ref = np.ascontiguousarray(reference, dtype=np.float32)
+    if ref.shape != (nsel, 3):
+        raise ValueError(f"reference must have shape ({nsel}, 3), got {ref.shape}")
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    if w is not None and w.shape != (nsel,):
+        raise ValueError("weights must have the same length as the selection")
+    lib = load()
+    if dev:
+        import torch
+        t = traj if (traj.dtype == torch.float32 and traj.is_contiguous()) else traj.to(torch.float32).contiguous()
+        d = t.device
+        rmsd = torch.empty((F,), dtype=torch.float64, device=d)
+        rot = torch.empty((F, 3, 3), dtype=torch.float64, device=d) if want_rotation else None
+        dst = None
+        if align:
+            dst = t if out is traj else (out if out is not None else torch.empty_like(t))
+        sel_d = None if sel is None else torch.as_tensor(sel, device=d)
+        ref_d = torch.as_tensor(ref, device=d)
+        w_d = None if w is None else torch.as_tensor(w, device=d)
+        check(lib.mdagpu_qcp_trajectory(tensor_ptr(t), F, natoms, tensor_ptr(sel_d), nsel,
+                                        tensor_ptr(ref_d), tensor_ptr(w_d), tensor_ptr(rmsd),
+                                        tensor_ptr(rot), tensor_ptr(dst), int(convention),
+                                        int(bool(allclose_shortcut)), DEVICE, current_stream(t)))
+        return rmsd, rot, dst
+    t = np.ascontiguousarray(traj, dtype=np.float32)
+    rmsd = np.empty((F,), dtype=np.float64)
+    rot = np.empty((F, 3, 3), dtype=np.float64) if want_rotation else None
+    dst = None
+    if align:
+        if out is traj and t is traj:
+            dst = t
+        else:
+            dst = out if out is not None else np.empty_like(t)
+    check(lib.mdagpu_qcp_trajectory(ptr(t), F, natoms, ptr(sel), nsel, ptr(ref), ptr(w), ptr(rmsd),
+                                    ptr(rot), ptr(dst), int(convention),
+                                    int(bool(allclose_shortcut)), HOST, None))
+    return rmsd, rot, dst

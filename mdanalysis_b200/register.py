@@ -1,0 +1,67 @@
+"""Plug the CUDA backend into an installed MDAnalysis.
+
+``MDAnalysis.lib.distances`` selects its low-level module with
+``_distances[backend.lower()]`` and ``getattr(module, funcname)``
+(``lib/distances.py:139-166``); adding one dictionary entry is therefore all it
+takes to make ``backend='cuda'`` work for ``distance_array``,
+``self_distance_array``, ``calc_bonds`` / ``calc_angles`` / ``calc_dihedrals``,
+``transform_RtoS/StoR`` and ``apply_PBC`` -- no source change, AtomGroup and
+AnalysisBase APIs untouched.  ``lib/_distopia.py:59-84`` is the precedent for a
+backend module.
+
+``capped_distance`` / ``self_capped_distance`` select by ``method=`` through
+local dictionaries (``lib/distances.py:557-560, 1023-1026``), so they cannot be
+extended from outside; ``install(patch_capped=True)`` swaps the two module-level
+functions for wrappers that keep the reference signature and add ``backend=``.
+"""
+from __future__ import annotations
+
+
+def install(patch_capped: bool = False, masquerade: str | None = None):
+    """Register ``backend='cuda'`` with MDAnalysis.  Returns the patched module.
+
+    masquerade  also install the module under an existing key (e.g. ``'serial'``)
+                so that the reference's own parametrised tests exercise the GPU
+                (option a).
+    """
+    import MDAnalysis.lib.distances as mda_distances
+
+    from .lib import c_distances_cuda
+    from .lib import distances as gpu_distances
+
+    mda_distances._distances["cuda"] = c_distances_cuda
+    if masquerade:
+        mda_distances._distances[masquerade] = c_distances_cuda
+    if patch_capped:
+        ref_capped = mda_distances.capped_distance
+        ref_self_capped = mda_distances.self_capped_distance
+
+        def capped_distance(reference, configuration, max_cutoff, min_cutoff=None, box=None,
+                            method=None, return_distances=True, backend="serial"):
+            if backend.lower() == "cuda":
+                return gpu_distances.capped_distance(reference, configuration, max_cutoff,
+                                                     min_cutoff=min_cutoff, box=box, method=method,
+                                                     return_distances=return_distances)
+            return ref_capped(reference, configuration, max_cutoff, min_cutoff=min_cutoff, box=box,
+                              method=method, return_distances=return_distances)
+
+        def self_capped_distance(reference, max_cutoff, min_cutoff=None, box=None, method=None,
+                                 return_distances=True, backend="serial"):
+            if backend.lower() == "cuda":
+                return gpu_distances.self_capped_distance(reference, max_cutoff,
+                                                          min_cutoff=min_cutoff, box=box,
+                                                          method=method,
+                                                          return_distances=return_distances)
+            return ref_self_capped(reference, max_cutoff, min_cutoff=min_cutoff, box=box,
+                                   method=method, return_distances=return_distances)
+
+        capped_distance.__doc__ = ref_capped.__doc__
+        self_capped_distance.__doc__ = ref_self_capped.__doc__
+        mda_distances.capped_distance = capped_distance
+        mda_distances.self_capped_distance = self_capped_distance
+    return mda_distances
+
+
+def uninstall():
+    import MDAnalysis.lib.distances as mda_distances
+    mda_distances._distances.pop("cuda", None)

@@ -1,0 +1,229 @@
+"""-m gpu: QCP / RMSD / AlignTraj / InterRDF / contacts through the C ABI vs the oracle."""
+import numpy as np
+import pytest
+
+from conftest import BOXES
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5        # BASELINE.json north_star: distances and RMSD within 1e-5 relative
+
+
+def make_traj(rng, F, N, noise=0.7):
+    ref = rng.normal(0, 12, (N, 3))
+    frames = []
+    for _ in range(F):
+        Q = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        if np.linalg.det(Q) < 0:
+            Q[:, 0] *= -1
+        frames.append(ref @ Q + rng.normal(0, 5, 3) + rng.normal(0, noise, (N, 3)))
+    return ref.astype(np.float32), np.asarray(frames, dtype=np.float32)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [3, 50, 1000, 20011])
+def test_calc_rmsd_rotational_matrix(oracle, dt, n):
+    from mdanalysis_b200.lib import qcprot
+    rng = np.random.default_rng(n)
+    x = rng.normal(0, 10, (n, 3))
+    y = x @ np.linalg.qr(rng.normal(size=(3, 3)))[0] + rng.normal(0, 1, (n, 3))
+    x, y = (x - x.mean(0)).astype(dt), (y - y.mean(0)).astype(dt)
+    w = rng.uniform(1, 16, n).astype(dt)
+    tol = 1e-10 if dt == np.float64 else 2e-3       # the reference's own float32 tolerance
+    for ww in (None, w):
+        r1, r2 = np.zeros(9, dtype=dt), np.zeros(9, dtype=dt)
+        v1 = qcprot.CalcRMSDRotationalMatrix(x, y, n, r1, ww)
+        v2 = oracle.CalcRMSDRotationalMatrix(x, y, n, r2, ww)
+        assert v1 == pytest.approx(v2, rel=tol)
+        assert np.allclose(r1, r2, atol=max(tol, 1e-9))
+        assert qcprot.CalcRMSDRotationalMatrix(x, y, n, None, ww) == pytest.approx(v2, rel=tol)
+
+
+def test_qcprot_known_answers():
+    """testsuite/MDAnalysisTests/lib/test_qcprot.py:35-46 (test_dummy)."""
+    from mdanalysis_b200.lib import qcprot
+    a = np.array([[1., 1., 1.], [2., 2., 2.]])
+    b = np.array([[0.1, 0.1, 0.1], [1.1, 1.1, 1.1]])
+    rot = np.zeros(9)
+    r = qcprot.CalcRMSDRotationalMatrix(a, b, 2, rot, None)
+    assert r == pytest.approx(0.7174389197644676, rel=1e-12)
+    assert np.allclose(rot.reshape(3, 3), np.eye(3), atol=1e-12)
+
+
+def test_rmsd_function(oracle):
+    from mdanalysis_b200.analysis.rms import rmsd
+    rng = np.random.default_rng(2)
+    a, b = rng.normal(0, 10, (100, 3)), rng.normal(0, 10, (100, 3))
+    w = rng.uniform(1, 3, 100)
+    assert rmsd(a, b, weights=w, superposition=True) == pytest.approx(oracle.rmsd(a, b, weights=w, superposition=True), rel=1e-12)
+    assert rmsd(a, b, center=True) == oracle.rmsd(a, b, center=True)
+    with pytest.raises(ValueError):
+        rmsd(a, b[:5])
+
+
+@pytest.mark.parametrize("N,F", [(301, 9), (10000, 6), (20000, 3)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_rmsd_trajectory(oracle, N, F, weighted):
+    from mdanalysis_b200.analysis.rms import RMSD
+    from mdanalysis_b200 import FrameBlock
+    rng = np.random.default_rng(N + F)
+    ref, traj = make_traj(rng, F, N)
+    masses = rng.uniform(1, 32, N)
+    blk = FrameBlock(traj, masses=masses)
+    R = RMSD(blk, FrameBlock(ref, masses=masses), weights="mass" if weighted else None).run()
+    want = oracle.rmsd_trajectory(traj, ref, weights=masses if weighted else None)
+    assert R.results.rmsd.shape == (F, 3)
+    assert np.array_equal(R.results.rmsd[:, 0], np.arange(F))
+    assert np.allclose(R.results.rmsd[:, 2], want, rtol=RTOL, atol=0)
+    assert np.allclose(R.results.rmsd[:, 2], want, rtol=1e-9, atol=0)      # what we actually reach
+    # frame slicing as AnalysisBase.run(start, stop, step)
+    R2 = RMSD(blk, FrameBlock(ref, masses=masses)).run(start=1, step=2)
+    assert np.array_equal(R2.results.rmsd[:, 0], np.arange(F)[1::2])
+    # device-resident input gives the same numbers
+    R3 = RMSD(blk.to_device(), FrameBlock(ref, masses=masses), weights="mass" if weighted else None).run()
+    assert np.array_equal(R3.results.rmsd, R.results.rmsd)
+
+
+def test_rmsd_selection_and_groups(oracle):
+    from mdanalysis_b200.analysis.rms import RMSD
+    rng = np.random.default_rng(77)
+    ref, traj = make_traj(rng, 5, 400)
+    sel = np.sort(rng.choice(400, 150, replace=False))
+    grp = np.sort(rng.choice(400, 60, replace=False))
+    R = RMSD(traj, ref, select=sel, groupselections=[grp]).run()
+    want = oracle.rmsd_trajectory(traj[:, sel], ref[sel])
+    assert np.allclose(R.results.rmsd[:, 2], want, rtol=1e-9)
+    # group RMSD after superposition on `sel` (rms.py:697-721), restated with the oracle pieces
+    for f in range(5):
+        com = traj[f, sel].astype(np.float64).mean(0)
+        ref_com = ref[sel].astype(np.float64).mean(0)
+        rot = np.zeros(9)
+        oracle.CalcRMSDRotationalMatrix((ref[sel] - ref_com).astype(np.float64),
+                                        traj[f, sel].astype(np.float64) - com, len(sel), rot, None)
+        x = traj[f].copy()
+        x -= com
+        x[:] = np.dot(x, rot.reshape(3, 3))
+        x += ref_com
+        g = np.sqrt(((x[grp].astype(np.float64) - ref[grp].astype(np.float64)) ** 2).sum() / len(grp))
+        assert R.results.rmsd[f, 3] == pytest.approx(g, rel=1e-6)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_align_trajectory(oracle, weighted):
+    from mdanalysis_b200.analysis.align import AlignTraj, rotation_matrix
+    from mdanalysis_b200 import FrameBlock
+    rng = np.random.default_rng(21)
+    ref, traj = make_traj(rng, 7, 1500)
+    traj[3] = ref                                   # exercises the np.allclose early exit
+    masses = rng.uniform(1, 32, 1500)
+    sel = np.arange(0, 1500, 3)
+    blk = FrameBlock(traj.copy(), masses=masses)
+    A = AlignTraj(blk, FrameBlock(ref, masses=masses), select=sel, weights="mass" if weighted else None).run()
+    want_xyz, want_rmsd = oracle.align_trajectory(traj, ref[sel], select=sel,
+                                                  weights=masses[sel] if weighted else None)
+    assert np.allclose(A.results.rmsd, want_rmsd, rtol=1e-9, atol=1e-12)
+    if not weighted:
+        assert A.results.rmsd[3] == 0.0
+    # the three float32 roundings are replicated: at most 1 ulp(float32) away
+    diff = np.abs(blk.positions - want_xyz)
+    assert diff.max() <= 4 * np.spacing(np.abs(want_xyz).max().astype(np.float32))
+    assert (diff > 0).mean() < 1e-3
+    R, v = rotation_matrix(traj[0, sel] - traj[0, sel].mean(0), ref[sel] - ref[sel].mean(0))
+    Ro, vo = oracle.rotation_matrix(traj[0, sel] - traj[0, sel].mean(0), ref[sel] - ref[sel].mean(0))
+    assert np.allclose(R, Ro, atol=1e-10) and v == pytest.approx(vo, rel=1e-10)
+
+
+@pytest.mark.parametrize("bname,rmax,nb", [("ortho", 6.0, 75), ("ortho", 12.0, 150), ("tric60", 6.0, 75),
+                                            ("tric60", 12.0, 150), ("tric", 9.0, 50)])
+@pytest.mark.parametrize("same", [True, False])
+def test_interrdf_counts_exact(oracle, bname, rmax, nb, same):
+    from mdanalysis_b200.analysis.rdf import InterRDF
+    from mdanalysis_b200 import FrameBlock
+    rng = np.random.default_rng(int(rmax) + nb)
+    box = BOXES[bname]
+    tv = oracle.triclinic_vectors(box).astype(np.float64)
+    F, N = 3, 700
+    pos = np.stack([(rng.random((N, 3)) * 1.4 - 0.2) @ tv for _ in range(F)]).astype(np.float32)
+    if same:
+        g1 = g2 = FrameBlock(pos, box)
+        a = b = pos
+    else:
+        a, b = np.ascontiguousarray(pos[:, :400]), np.ascontiguousarray(pos[:, 250:])
+        g1, g2 = FrameBlock(a, box), FrameBlock(b, box)
+    try:
+        want = oracle.interrdf(a, b, box, nbins=nb, rrange=(0.0, rmax))
+    except ValueError:
+        with pytest.raises(ValueError):
+            InterRDF(g1, g2, nbins=nb, range=(0.0, rmax)).run()
+        return
+    got = InterRDF(g1, g2, nbins=nb, range=(0.0, rmax)).run()
+    assert np.array_equal(got.results.edges, want["edges"])
+    assert np.array_equal(got.results.bins, want["bins"])
+    assert np.array_equal(got.results.count, want["count"])        # bit-exact integer counts
+    assert np.allclose(got.results.rdf, want["rdf"], rtol=1e-12)
+    if same:
+        assert got.results.count[0] >= F * N                        # self pairs land in bin 0
+
+
+def test_interrdf_large_nsgrid_path(oracle):
+    """n*m >= 1e8 forces the reference's nsgrid method (lazy minimum image)."""
+    from mdanalysis_b200.analysis.rdf import InterRDF
+    from mdanalysis_b200 import FrameBlock
+    rng = np.random.default_rng(1)
+    N, L = 10001, 66.0
+    box = np.array([L, L, L, 90, 90, 90], dtype=np.float32)
+    pos = (rng.random((2, N, 3)) * L * 1.2 - 0.1 * L).astype(np.float32)
+    blk = FrameBlock(pos, box)
+    got = InterRDF(blk, blk, nbins=150, range=(0.0, 15.0)).run()
+    want = oracle.interrdf(pos, pos, box, nbins=150, rrange=(0.0, 15.0))
+    assert np.array_equal(got.results.count, want["count"])
+    got2 = InterRDF(blk.to_device(), None, nbins=150, range=(0.0, 15.0), exclusion_block=(1, 1)).run()
+    want2 = oracle.interrdf(pos, pos, box, nbins=150, rrange=(0.0, 15.0), exclusion_block=(1, 1))
+    assert np.array_equal(got2.results.count, want2["count"])
+    assert np.allclose(got2.results.rdf, want2["rdf"], rtol=1e-12)
+    assert got2.results.count[0] == want["count"][0] - 2 * N
+
+
+def test_interrdf_known_answers():
+    """testsuite/MDAnalysisTests/analysis/test_rdf.py:39-136: two hand-placed waters."""
+    from mdanalysis_b200.analysis.rdf import InterRDF
+    from mdanalysis_b200 import FrameBlock
+    x, y = [1] * 3 + [2] * 3, [2, 1, 3] * 2
+    pos = np.array([[[a, b, 0.0] for a, b in zip(x, y)]], dtype=np.float32)
+    box = np.array([100, 100, 100, 90, 90, 90], dtype=np.float32)
+    s1 = FrameBlock(pos[:, [0, 3]], box)             # name OW
+    s2 = FrameBlock(pos[:, [1, 2, 4, 5]], box)       # name HW1 HW2
+    rdf = InterRDF(s1, s2).run()
+    assert rdf.results.count.sum() == 8                                   # :69-74
+    assert len(rdf.results.count[rdf.results.count == 4]) == 2            # :77-81
+    rdf.run()                                                             # :84-89 double run
+    assert len(rdf.results.count[rdf.results.count == 4]) == 2
+    assert InterRDF(s1, s2, exclusion_block=(1, 2)).run().results.count.sum() == 4   # :92-96
+    assert len(InterRDF(s1, s2, nbins=412).run().results.bins) == 412     # :52-57
+    r = InterRDF(s1, s2, range=(1.0, 13.0)).run()                         # :60-66
+    assert r.results.edges[0] == 1.0 and r.results.edges[-1] == 13.0
+    for norm, value in (("density", 1.956823), ("rdf", 244602.88385), ("none", 4)):   # :129-136
+        assert max(InterRDF(s1, s2, norm=norm).run().results.rdf) == pytest.approx(value, rel=1e-6)
+    with pytest.raises(ValueError, match="invalid norm"):
+        InterRDF(s1, s2, norm="foo")
+    with pytest.raises(ValueError, match="The exclude_same argument to InterRDF must be"):
+        InterRDF(s2, s2, exclude_same="unsupported")
+
+
+def test_self_contacts(oracle):
+    from mdanalysis_b200.analysis.contacts import self_contacts, contact_matrix
+    rng = np.random.default_rng(15)
+    F, n = 3, 2500
+    pos = (rng.random((F, n, 3)) * 60 * 1.5 - 10).astype(np.float32)
+    for box in (None, np.array([60, 60, 60, 90, 90, 90], dtype=np.float32), BOXES["tric60"]):
+        counts, deg = self_contacts(pos, 8.0, box=box, return_degree=True)
+        for f in range(F):
+            d = oracle.self_distance_array(pos[f], box)
+            assert counts[f] == (d <= 8.0).sum()
+            iu = np.triu_indices(n, 1)
+            hit = d <= 8.0
+            want_deg = np.bincount(iu[0][hit], minlength=n) + np.bincount(iu[1][hit], minlength=n)
+            assert np.array_equal(deg[f], want_deg)
+    import torch
+    c2 = self_contacts(torch.as_tensor(pos).cuda(), 8.0)
+    assert np.array_equal(c2.cpu().numpy().astype(np.uint64), self_contacts(pos, 8.0))
+    assert contact_matrix(np.array([1.0, 8.0, 8.1]), 8.0).tolist() == [True, True, False]
