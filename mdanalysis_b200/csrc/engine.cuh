@@ -148,6 +148,7 @@ struct SearchParams {
     float d2_filter;     // FP32 rejection threshold (>= d2_max * (1 + band))
     int use_filter;      // 0 for flavours without a safe FP32 bound
     int stencil;         // 1: 27/13-cell stencil; 0: single cell (all pairs)
+    int include_self;    // SELF traversals: also report the pair (i, i)  (capped_distance(x, x))
 };
 
 // One thread per query, in cell-sorted order.  `Sink` receives every accepted
@@ -218,6 +219,101 @@ pair_search_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restric
     sink.end();
 }
 
+// ---- tiled traversal: one CTA per home cell --------------------------------------------
+// For dense cells (tens of atoms or more, e.g. the RDF workload) the candidates of a
+// neighbour cell are staged once per CTA in shared memory with coalesced 16-byte
+// loads and every thread (one query of the home cell each) walks the tile with
+// warp-broadcast LDS.128 reads: no per-lane global-load latency, uniform trip
+// counts, no divergence.  blockIdx.x = cell * chunks + chunk, blockIdx.y = frame.
+//   SELF = true : the home cell contributes only later slots and the 13-cell half
+//                 shell is visited, i.e. every unordered pair is seen once; the sink
+//                 is told via hit_sym()/try_fast_sym() that the pair stands for both
+//                 orders (InterRDF of a group with itself, self_search, contacts).
+constexpr int TILE_ATOMS = 256;
+
+template <int MIC, bool SELF, class Sink>
+__global__ void __launch_bounds__(Sink::THREADS)
+cell_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
+                 const float4 *__restrict__ c_atoms, const uint32_t *__restrict__ c_start,
+                 const FrameGeom *__restrict__ fgs, int per_frame, int chunks, SearchParams sp,
+                 Sink sink)
+{
+    constexpr int T = Sink::THREADS;
+    __shared__ FrameGeom sfg;
+    __shared__ float4 tile[TILE_ATOMS];
+    const uint64_t f = blockIdx.y;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(fgs + (per_frame ? f : 0));
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sfg);
+        for (int w = threadIdx.x; w < (int)(sizeof(FrameGeom) / 4); w += T) dst[w] = src[w];
+    }
+    sink.begin();
+    __syncthreads();
+    const int64_t cell = blockIdx.x / chunks;
+    if (cell >= sfg.grid.ncell_total) return;                 // uniform: frames may have fewer cells
+    const int chunk0 = blockIdx.x % chunks;
+    const BoxParams box = sfg.box;
+    const int64_t base = per_frame ? sfg.cell_base : (int64_t)f * sfg.grid.ncell_total;
+    int cx = 0, cy = 0, cz = 0;
+    if (sp.stencil) {
+        cx = (int)(cell % sfg.grid.ncells[0]);
+        const int64_t r = cell / sfg.grid.ncells[0];
+        cy = (int)(r % sfg.grid.ncells[1]);
+        cz = (int)(r / sfg.grid.ncells[1]);
+    }
+    const uint32_t q0 = q_start[base + cell], q1 = q_start[base + cell + 1];
+    const int nsten = sp.stencil ? (SELF ? 14 : 27) : 1;
+    for (uint32_t qbase = q0 + (uint32_t)chunk0 * T; qbase < q1; qbase += (uint32_t)chunks * T) {
+        const uint32_t qslot = qbase + threadIdx.x;
+        const bool active = qslot < q1;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) q = q_atoms[qslot];
+        const int qi = __float_as_int(q.w);
+        if (SELF && sp.include_self && active) {
+            const double d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, q.x, q.y, q.z, box);
+            if (d2 <= sp.d2_max && d2 > sp.d2_min) sink.template hit_w<SELF>(qi, qi, d2, f);
+        }
+        for (int s = 0; s < nsten; ++s) {
+            int64_t ncell;
+            if (!sp.stencil) ncell = 0;
+            else if (SELF) {
+                const unsigned r = kSelfRoute[s];
+                ncell = cell_neighbor(sfg.grid, cx + (int)(r & 3u) - 1, cy + (int)((r >> 2) & 3u) - 1,
+                                      cz + (int)((r >> 4) & 3u) - 1);
+            } else {
+                ncell = cell_neighbor(sfg.grid, cx + s / 9 - 1, cy + (s / 3) % 3 - 1, cz + s % 3 - 1);
+            }
+            if (ncell < 0) continue;
+            uint32_t j0 = c_start[base + ncell];
+            const uint32_t j1 = c_start[base + ncell + 1];
+            // home cell of a SELF search: only slots after the first query of this chunk matter
+            if (SELF && s == 0 && j0 < qbase + 1) j0 = qbase + 1;
+            for (uint32_t tb = j0; tb < j1; tb += TILE_ATOMS) {
+                const int tn = (int)min((uint32_t)TILE_ATOMS, j1 - tb);
+                __syncthreads();
+                for (int k = threadIdx.x; k < tn; k += T) tile[k] = c_atoms[tb + k];
+                __syncthreads();
+                if (!active) continue;
+                int k = 0;
+                if (SELF && s == 0 && qslot + 1 > tb) k = (int)(qslot + 1 - tb);   // later slots only
+#pragma unroll 4
+                for (; k < tn; ++k) {
+                    const float4 c = tile[k];
+                    const float tx = q.x - c.x, ty = q.y - c.y, tz = q.z - c.z;     // a - b (nsgrid.pyx:486-488)
+                    if (sp.use_filter) {
+                        const float d2f = pair_d2_filter<MIC>(tx, ty, tz, box);
+                        if (d2f > sp.d2_filter) continue;
+                        if (Sink::FAST && sink.template try_fast_w<SELF>(qi, __float_as_int(c.w), d2f)) continue;
+                    }
+                    const double d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, c.x, c.y, c.z, box);
+                    if (d2 <= sp.d2_max && d2 > sp.d2_min) sink.template hit_w<SELF>(qi, __float_as_int(c.w), d2, f);
+                }
+            }
+        }
+    }
+    sink.end();
+}
+
 // ---- sinks -----------------------------------------------------------------------------
 // Appends (i, j, sqrt(d2)) with one atomic per converged group of lanes.
 struct PairSink {
@@ -229,6 +325,8 @@ struct PairSink {
     int orient;                       // 1: emit (min(i,j), max(i,j))  (brute-force self variant)
     static constexpr bool FAST = false;
     __device__ __forceinline__ bool try_fast(int, int, float) { return false; }
+    template <bool SYM> __device__ __forceinline__ bool try_fast_w(int, int, float) { return false; }
+    template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t f) { hit(i, j, d2, f); }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void end() {}
     __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t)

@@ -411,6 +411,7 @@ extern "C" int mdagpu_grid_search(mdagpu_grid *g, const float *queries, uint64_t
         sp.d2_filter = filter_threshold(sp.d2_max, g->mic == MIC_TRICLINIC ? tric_abs_err(g->fg.box.h) : 0.0);
         sp.use_filter = 1;
         sp.stencil = 1;
+        sp.include_self = 0;
         rc = dispatch_pair_search<false>(g->mic, ql, nq, g->cl, g->fg_dev, sp,
                                          guess_pairs(nq, g->n, g->cutoff, grid_volume(g)), 0, st, res);
     }
@@ -433,6 +434,7 @@ extern "C" int mdagpu_grid_self_search(mdagpu_grid *g, mdagpu_stream_t stream, m
     sp.d2_filter = filter_threshold(sp.d2_max, g->mic == MIC_TRICLINIC ? tric_abs_err(g->fg.box.h) : 0.0);
     sp.use_filter = 1;
     sp.stencil = 1;
+    sp.include_self = 0;
     int rc = dispatch_pair_search<true>(g->mic, g->cl, g->n, g->cl, g->fg_dev, sp,
                                         guess_pairs(g->n, g->n, g->cutoff, grid_volume(g)) / 2 + 4096, 0, st, res);
     if (rc != MDAGPU_OK) { delete res; return rc; }
@@ -509,6 +511,7 @@ extern "C" int mdagpu_capped_bruteforce(const float *ref, uint64_t n, const floa
         sp.d2_filter = filter_threshold(sp.d2_max, box_mode == BOX_TRICLINIC ? tric_abs_err(fg.box.h) : 0.0);
         sp.use_filter = box_mode != BOX_ORTHO;   // no safe FP32 bound for unwrapped ortho input
         sp.stencil = 0;
+        sp.include_self = 0;
         const int mic = box_mode == BOX_ORTHO ? MIC_ORTHO_ROUND : (box_mode == BOX_TRICLINIC ? MIC_TRICLINIC : MIC_NONE);
         const uint64_t guess = (self ? n * 32 : n * 64) + 4096;
         if (self) rc = dispatch_pair_search<true>(mic, rl, n, rl, fg_dev.as<FrameGeom>(), sp, guess, 1, st, res);

@@ -68,18 +68,48 @@ struct HistSink {
         const int nwords = (nbins + 1) >> 1;
         for (int w = threadIdx.x; w < nwords * T; w += T) s_hist[w] = 0u;
     }
-    __device__ __forceinline__ void add(int k)
+    __device__ __forceinline__ void add(int k, uint32_t weight = 1u)
     {
         uint32_t *w = column() + (k >> 1) * T;
         const uint32_t sh = (uint32_t)(k & 1) << 4;
         uint32_t v = *w;
-        if (((v >> sh) & 0xffffu) == 0xffffu) {
-            atomicAdd(&counts[k], 65536ull);    // 65535 stored + this one
+        const uint32_t cur = (v >> sh) & 0xffffu;
+        if (cur + weight > 0xffffu) {            // would wrap: flush this counter
+            atomicAdd(&counts[k], (unsigned long long)(cur + weight));
             v &= ~(0xffffu << sh);
         } else {
-            v += 1u << sh;
+            v += weight << sh;
         }
         *w = v;
+    }
+    // an unordered pair seen once stands for (i,j) and (j,i)
+    template <bool SYM> __device__ __forceinline__ uint32_t weight_of(int i, int j) const
+    {
+        if (!SYM) return excluded(i, j) ? 0u : 1u;
+        if (i == j) return excluded(i, i) ? 0u : 1u;
+        return (excluded(i, j) ? 0u : 1u) + (excluded(j, i) ? 0u : 1u);
+    }
+    template <bool SYM> __device__ __forceinline__ bool try_fast_w(int i, int j, float d2f)
+    {
+        if (!(d2f < d2_fast_max)) return false;
+        const float u = (sqrtf(d2f) - lo) * inv_dr;
+        const float fk = floorf(u);
+        const float frac = u - fk;
+        if (!(frac > band && frac < 1.0f - band) || !(u > 0.0f) || !(fk < (float)nbins)) return false;
+        const uint32_t wgt = weight_of<SYM>(i, j);
+        if (wgt) add((int)fk, wgt);
+        return true;
+    }
+    template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t)
+    {
+        const uint32_t wgt = weight_of<SYM>(i, j);
+        if (!wgt) return;
+        if (!(d2 >= thr[0]) || !(d2 <= thr[nbins])) return;
+        int k = (int)((sqrtf((float)d2) - lo) * inv_dr);
+        k = k < 0 ? 0 : (k > nbins - 1 ? nbins - 1 : k);
+        while (k > 0 && d2 < thr[k]) --k;
+        while (k < nbins - 1 && d2 >= thr[k + 1]) ++k;
+        add(k, wgt);
     }
     __device__ __forceinline__ bool excluded(int i, int j) const
     {
@@ -115,7 +145,11 @@ struct HistSink {
             const uint32_t *row = s_hist + (k >> 1) * T;
             const uint32_t sh = (uint32_t)(k & 1) << 4;
             unsigned long long sum = 0;
-            for (int u = 0; u < T; ++u) sum += (row[(u + threadIdx.x) & (T - 1)] >> sh) & 0xffffu;
+            for (int u = 0; u < T; ++u) {
+                int c = u + (int)threadIdx.x;
+                if (c >= T) c -= T;                       // skewed walk: 32 distinct banks per warp
+                sum += (row[c] >> sh) & 0xffffu;
+            }
             if (sum) atomicAdd(&counts[k], sum);
         }
     }
@@ -130,18 +164,26 @@ struct HistSinkGlobal {
     int nbins, excl_a, excl_b;
     float lo, inv_dr, band, d2_fast_max;
     __device__ __forceinline__ bool try_fast(int, int, float) { return false; }
+    template <bool SYM> __device__ __forceinline__ bool try_fast_w(int, int, float) { return false; }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void end() {}
-    __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t)
+    __device__ __forceinline__ bool excluded(int i, int j) const
     {
-        if (excl_a > 0 && (i / excl_a) == (j / excl_b)) return;
+        return excl_a > 0 && (i / excl_a) == (j / excl_b);
+    }
+    template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t)
+    {
+        unsigned long long wgt = excluded(i, j) ? 0ull : 1ull;
+        if (SYM && i != j) wgt += excluded(j, i) ? 0ull : 1ull;
+        if (!wgt) return;
         if (!(d2 >= thr[0]) || !(d2 <= thr[nbins])) return;
         int k = (int)((sqrtf((float)d2) - lo) * inv_dr);
         k = k < 0 ? 0 : (k > nbins - 1 ? nbins - 1 : k);
         while (k > 0 && d2 < thr[k]) --k;
         while (k < nbins - 1 && d2 >= thr[k + 1]) ++k;
-        atomicAdd(&counts[k], 1ull);
+        atomicAdd(&counts[k], wgt);
     }
+    __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t f) { hit_w<false>(i, j, d2, f); }
 };
 
 // contacts: pair count per frame and optional per-atom degree
@@ -153,6 +195,8 @@ struct CountSink {
     uint64_t n;
     unsigned local;
     __device__ __forceinline__ bool try_fast(int, int, float) { return false; }
+    template <bool SYM> __device__ __forceinline__ bool try_fast_w(int, int, float) { return false; }
+    template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t f) { hit(i, j, d2, f); }
     __device__ __forceinline__ void begin() { local = 0; }
     __device__ __forceinline__ void hit(int i, int j, double, uint64_t f)
     {
@@ -171,32 +215,38 @@ struct CountSink {
     }
 };
 
-template <int MIC, class Sink>
-static int launch_hist(const CellList &ql, uint64_t nq, const CellList &cl, const FrameGeom *fg_dev,
-                       int per_frame, uint64_t nframes, const SearchParams &sp, const Sink &sink,
-                       size_t smem, cudaStream_t st)
+template <int MIC, bool SELF, class Sink>
+static int launch_hist(const CellList &ql, const CellList &cl, const FrameGeom *fg_dev, int per_frame,
+                       uint64_t nframes, uint64_t grid_x, int chunks, const SearchParams &sp,
+                       const Sink &sink, size_t smem, cudaStream_t st)
 {
-    auto kern = pair_search_kernel<MIC, false, Sink>;
-    if (smem > 48 * 1024)
+    auto kern = cell_tile_kernel<MIC, SELF, Sink>;
+    if (smem > 32 * 1024)
         MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(cdiv(nq, Sink::THREADS), (unsigned)nframes);
-    MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, smem, st, ql.atoms(), ql.key_of_sorted(), nq,
-                  cl.atoms(), cl.start(), fg_dev, per_frame, sp, sink);
+    dim3 grid((unsigned)grid_x, (unsigned)nframes);
+    MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, smem, st, ql.atoms(), ql.start(),
+                  cl.atoms(), cl.start(), fg_dev, per_frame, chunks, sp, sink);
     MDA_CHECK_LAUNCH();
     return MDAGPU_OK;
 }
 
 template <class Sink>
-static int dispatch_hist(int mic, const CellList &ql, uint64_t nq, const CellList &cl,
-                         const FrameGeom *fg_dev, int per_frame, uint64_t nframes,
-                         const SearchParams &sp, const Sink &sink, size_t smem, cudaStream_t st)
+static int dispatch_hist(int mic, bool self, const CellList &ql, const CellList &cl,
+                         const FrameGeom *fg_dev, int per_frame, uint64_t nframes, uint64_t grid_x,
+                         int chunks, const SearchParams &sp, const Sink &sink, size_t smem,
+                         cudaStream_t st)
 {
+#define HIST_CASE(M)                                                                               \
+    case M:                                                                                        \
+        return self ? launch_hist<M, true>(ql, cl, fg_dev, per_frame, nframes, grid_x, chunks, sp, sink, smem, st) \
+                    : launch_hist<M, false>(ql, cl, fg_dev, per_frame, nframes, grid_x, chunks, sp, sink, smem, st)
     switch (mic) {
-    case MIC_NONE: return launch_hist<MIC_NONE>(ql, nq, cl, fg_dev, per_frame, nframes, sp, sink, smem, st);
-    case MIC_ORTHO_ROUND: return launch_hist<MIC_ORTHO_ROUND>(ql, nq, cl, fg_dev, per_frame, nframes, sp, sink, smem, st);
-    case MIC_ORTHO_LAZY: return launch_hist<MIC_ORTHO_LAZY>(ql, nq, cl, fg_dev, per_frame, nframes, sp, sink, smem, st);
-    case MIC_TRICLINIC: return launch_hist<MIC_TRICLINIC>(ql, nq, cl, fg_dev, per_frame, nframes, sp, sink, smem, st);
+        HIST_CASE(MIC_NONE);
+        HIST_CASE(MIC_ORTHO_ROUND);
+        HIST_CASE(MIC_ORTHO_LAZY);
+        HIST_CASE(MIC_TRICLINIC);
     }
+#undef HIST_CASE
     return set_error(MDAGPU_ERR_INVALID, "unknown minimum-image flavour %d", mic);
 }
 
@@ -340,16 +390,31 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
         }
         const CellList &qq = same ? cl : ql;
         const int nwords = (nbins + 1) / 2;
-        if ((size_t)nwords * 256 * 4 <= 100 * 1024) {
-            HistSink<256> sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, lo, inv_dr, band, d2_fast_max };
-            rc = dispatch_hist(mic, qq, na, cl, fgd, boxes_per_frame, fc, sp, sink, (size_t)nwords * 256 * 4, st);
-        } else if ((size_t)nwords * 64 * 4 <= 200 * 1024) {
-            HistSink<64> sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, lo, inv_dr, band, d2_fast_max };
-            rc = dispatch_hist(mic, qq, na, cl, fgd, boxes_per_frame, fc, sp, sink, (size_t)nwords * 64 * 4, st);
-        } else {
-            HistSinkGlobal sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, lo, inv_dr, band, d2_fast_max };
-            rc = dispatch_hist(mic, qq, na, cl, fgd, boxes_per_frame, fc, sp, sink, 0, st);
+        // threads per CTA ~ atoms per home cell (one query per thread)
+        const uint64_t max_cells = boxes_per_frame ? total_cells / fc + 1 : (uint64_t)cells_per_frame;
+        const double occupancy = use_grid ? (double)na * (double)fc / (double)total_cells : (double)na;
+        int threads = occupancy > 128.0 ? 192 : (occupancy > 64.0 ? 128 : 64);
+        while (threads > 64 && (size_t)nwords * threads * 4 > 160 * 1024) threads = threads == 192 ? 128 : 64;
+        const bool fits = (size_t)nwords * threads * 4 <= 160 * 1024;
+        if (!fits) threads = 128;
+        int chunks = 1;
+        uint64_t grid_x = max_cells;
+        if (!use_grid) {                         // single cell: split the queries over CTAs
+            chunks = (int)((na + threads - 1) / threads);
+            grid_x = (uint64_t)chunks;
         }
+        SearchParams spc = sp;
+        spc.include_self = same ? 1 : 0;
+#define RUN_HIST(SINK, SMEM)                                                                        \
+    do {                                                                                           \
+        SINK sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, lo, inv_dr, band, d2_fast_max }; \
+        rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, grid_x, chunks, spc, sink, SMEM, st); \
+    } while (0)
+        if (!fits) RUN_HIST(HistSinkGlobal, 0);
+        else if (threads == 192) RUN_HIST(HistSink<192>, (size_t)nwords * 192 * 4);
+        else if (threads == 128) RUN_HIST(HistSink<128>, (size_t)nwords * 128 * 4);
+        else RUN_HIST(HistSink<64>, (size_t)nwords * 64 * 4);
+#undef RUN_HIST
         if (rc) return rc;
     }
     MDA_CUDA(cnt.finish());

@@ -99,7 +99,8 @@ def test_known_answers(gd):
     assert dists == pytest.approx([0.0, 1.7320508075688772, 11.0, 104.26888318])
     dists = gd.calc_bonds(a, b, box=box)
     assert dists == pytest.approx([0.0, 1.7320508075688772, 1.0, 3.46410072])
-    tbox = np.array([10., 10., 10., 60., 60., 60.], dtype=np.float32)
+    from mdanalysis_b200.lib import mdamath
+    tbox = mdamath.triclinic_box([10., 0., 0.], [1., 10., 0.], [1., 0., 10.])     # :887-891
     dists = gd.calc_bonds(a, b, box=tbox)
     assert dists == pytest.approx([0.0, 1.7320508, 1.4142136, 2.82842712], abs=1e-6)
 
