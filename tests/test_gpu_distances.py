@@ -102,7 +102,8 @@ def test_known_answers(gd):
     from mdanalysis_b200.lib import mdamath
     tbox = mdamath.triclinic_box([10., 0., 0.], [1., 10., 0.], [1., 0., 10.])     # :887-891
     dists = gd.calc_bonds(a, b, box=tbox)
-    assert dists == pytest.approx([0.0, 1.7320508, 1.4142136, 2.82842712], abs=1e-6)
+    # reference tolerance: assert_almost_equal(..., prec=5)  (test_distances.py:878, :969-975)
+    assert dists == pytest.approx([0.0, 1.7320508, 1.4142136, 2.82842712], abs=1.5e-5)
 
 
 @pytest.mark.parametrize("bname", list(BOXES))
