@@ -7,15 +7,22 @@
 //                                                     -> convention 1
 //   core/groups.py:1083-1106 center(), :1478-1529 translate()/rotate()
 //
-// One CTA per frame.  The selected atoms of the frame are read from HBM once,
-// parked in shared memory as float32 (10 000 atoms = 120 kB), and used twice:
-// pass 1 accumulates the (weighted) centre in float64, pass 2 the 3x3 inner
-// product and G1 of the centred float64 coordinates, exactly the quantities the
-// reference forms (it also centres in float64 before calling QCP).  A warp
-// shuffle + shared-memory tree reduces the 10 sums; one thread then runs the
-// Newton-Raphson quartic solve and the adjugate/quaternion step.  With
-// `aligned`, all threads apply the rigid transform to every atom of the frame
-// (the frame is still L2-resident) with the reference's three float32 roundings.
+// One CTA per frame, several CTAs per SM.  Every frame is read from HBM exactly
+// once, with 16-byte loads where the layout allows (natoms % 4 == 0, contiguous
+// selection): a thread owns "quads" of 4 atoms = 3 float4.  A single pass
+// accumulates, in float64 and relative to a per-frame pivot (the first fitted atom,
+// which removes the translation from the magnitudes that are summed),
+//     Sy = sum w y',  M = sum w y' (x - x_com)^T,  G = sum w |y'|^2 ,   y' = y - pivot
+// from which the centred quantities the reference forms (it centres in float64
+// before calling QCP, rms.py:685-701) follow exactly:
+//     y_com = pivot + Sy/W,  A = M - (Sy/W) (sum w (x - x_com))^T,  G1 = G - |Sy|^2/W.
+// The centred (and weight-scaled) reference is prepared once per call in float64
+// (qcp_ref_kernel) and is read through L1/L2 by every CTA.  A warp shuffle +
+// shared-memory tree reduces the 13 sums; one thread runs the Newton-Raphson quartic
+// solve and the adjugate/quaternion step (geom.cuh qcp_solve) while the other CTAs
+// of the SM keep streaming.  With `aligned`, the CTA re-reads its frame (still in
+// L2: at most a few frames per SM are in flight) and applies the rigid transform
+// to every atom with the reference's three float32 roundings.
 #include "common.cuh"
 
 namespace mdagpu {
@@ -25,6 +32,9 @@ constexpr int QCP_THREADS = 512;
 struct RefInfo {       // produced once per call by qcp_ref_kernel
     double com[3];
     double g2;         // sum_i w_i |ref_i - com|^2
+    double sx[3];      // sum_i w_i (ref_i - com): zero up to rounding, kept for rigour
+    double wsum;       // sum_i w_i (nsel without weights)
+    double close_sum;  // sum_i,k (1e-8 + 1e-5 |ref_ik - com_k|)^2 : screen for np.allclose (align.py:290)
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -56,12 +66,13 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double *scratch /* [K 
     __syncthreads();
 }
 
-// centre and G2 of the reference selection
+// centre, G2 and the centred float64 copy of the reference selection:
+// refc[3i+k] = w_i * (ref_i - com)_k  (w_i = 1 without weights), sx = sum_i refc[i]
 __global__ void __launch_bounds__(QCP_THREADS)
 qcp_ref_kernel(const float *__restrict__ ref, const double *__restrict__ w, uint64_t nsel,
-               RefInfo *__restrict__ out)
+               RefInfo *__restrict__ out, double *__restrict__ refc)
 {
-    __shared__ double scratch[4 * (QCP_THREADS / 32)];
+    __shared__ double scratch[5 * (QCP_THREADS / 32)];
     double s[4] = { 0.0, 0.0, 0.0, 0.0 };
     for (uint64_t i = threadIdx.x; i < nsel; i += QCP_THREADS) {
         const double wi = w ? w[i] : 1.0;
@@ -72,98 +83,144 @@ qcp_ref_kernel(const float *__restrict__ ref, const double *__restrict__ w, uint
     }
     block_sum<4, QCP_THREADS>(s, scratch);
     const double cx = s[0] / s[3], cy = s[1] / s[3], cz = s[2] / s[3];
-    double g[1] = { 0.0 };
+    double g[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
     for (uint64_t i = threadIdx.x; i < nsel; i += QCP_THREADS) {
         const double wi = w ? w[i] : 1.0;
         const double x = (double)ref[3 * i] - cx, y = (double)ref[3 * i + 1] - cy, z = (double)ref[3 * i + 2] - cz;
         g[0] = fma(wi, x * x + y * y + z * z, g[0]);
+        const double wx = wi * x, wy = wi * y, wz = wi * z;
+        refc[3 * i] = wx; refc[3 * i + 1] = wy; refc[3 * i + 2] = wz;
+        g[1] += wx; g[2] += wy; g[3] += wz;
+        const double tx = 1e-8 + 1e-5 * fabs(x), ty = 1e-8 + 1e-5 * fabs(y), tz = 1e-8 + 1e-5 * fabs(z);
+        g[4] += tx * tx + ty * ty + tz * tz;
     }
-    block_sum<1, QCP_THREADS>(g, scratch);
+    block_sum<5, QCP_THREADS>(g, scratch);
     if (threadIdx.x == 0) {
         out->com[0] = cx; out->com[1] = cy; out->com[2] = cz;
         out->g2 = g[0];
+        out->sx[0] = g[1]; out->sx[1] = g[2]; out->sx[2] = g[3];
+        out->wsum = s[3];
+        out->close_sum = g[4];
     }
 }
 
-template <bool WEIGHTED, bool STAGE>
-__global__ void __launch_bounds__(QCP_THREADS)
-qcp_traj_kernel(const float *traj, uint64_t natoms, const int32_t *__restrict__ sel,
-                uint64_t nsel, const float *__restrict__ ref, const double *__restrict__ w,
-                const RefInfo *__restrict__ refinfo, double *__restrict__ rmsd_out,
-                double *__restrict__ rot_out, float *aligned, int convention,
-                int allclose_shortcut)
+// accumulate one atom: y' = y - pivot (exact in double), xw = w (x - x_com)
+template <bool WEIGHTED>
+__device__ __forceinline__ void qcp_accumulate(double (&acc)[13], float fx, float fy, float fz,
+                                               double px, double py, double pz, double xw0, double xw1,
+                                               double xw2, double wi)
 {
-    extern __shared__ float s_xyz[];                       // [nsel*3] when STAGE
-    __shared__ double scratch[11 * (QCP_THREADS / 32)];
+    const double y0 = (double)fx - px, y1 = (double)fy - py, y2 = (double)fz - pz;
+    acc[0] = fma(y0, xw0, acc[0]); acc[1] = fma(y0, xw1, acc[1]); acc[2] = fma(y0, xw2, acc[2]);
+    acc[3] = fma(y1, xw0, acc[3]); acc[4] = fma(y1, xw1, acc[4]); acc[5] = fma(y1, xw2, acc[5]);
+    acc[6] = fma(y2, xw0, acc[6]); acc[7] = fma(y2, xw1, acc[7]); acc[8] = fma(y2, xw2, acc[8]);
+    if (WEIGHTED) {
+        const double w0 = wi * y0, w1 = wi * y1, w2 = wi * y2;
+        acc[9] = fma(w0, y0, fma(w1, y1, fma(w2, y2, acc[9])));
+        acc[10] += w0; acc[11] += w1; acc[12] += w2;
+    } else {
+        acc[9] = fma(y0, y0, fma(y1, y1, fma(y2, y2, acc[9])));
+        acc[10] += y0; acc[11] += y1; acc[12] += y2;
+    }
+}
+
+// np.allclose(mobile - mobile_com, ref - ref_com) of align.rotation_matrix (align.py:290):
+// |a - b| <= 1e-8 + 1e-5 |b| for every component.  Needs the centres, hence its own pass
+// (only AlignTraj without weights asks for it; the frame is L2-resident by then).
+__device__ __forceinline__ bool qcp_close(double y, double x)
+{
+    return fabs(y - x) <= 1e-8 + 1e-5 * fabs(x);
+}
+
+template <int T, bool WEIGHTED, bool VEC>
+__global__ void __launch_bounds__(T)
+qcp_traj_kernel(const float *traj, uint64_t natoms, const int32_t *__restrict__ sel, uint64_t nsel,
+                const double *__restrict__ refc, const double *__restrict__ w,
+                const RefInfo *__restrict__ refinfo, double *__restrict__ rmsd_out,
+                double *__restrict__ rot_out, float *aligned, int convention, int allclose_shortcut)
+{
+    __shared__ double scratch[13 * (T / 32)];
     __shared__ double s_rot[9];
     __shared__ double s_com[3];
     const uint64_t f = blockIdx.x;
     const float *frame = traj + f * natoms * 3;
+    const uint64_t a0 = sel ? (uint64_t)sel[0] : 0;
+    const double px = (double)frame[3 * a0], py = (double)frame[3 * a0 + 1], pz = (double)frame[3 * a0 + 2];
 
-    // ---- pass 1: centre of the mobile selection (float64) ------------------------
-    double c[4] = { 0.0, 0.0, 0.0, 0.0 };
-    for (uint64_t i = threadIdx.x; i < nsel; i += QCP_THREADS) {
-        const uint64_t a = sel ? (uint64_t)sel[i] : i;
-        const float x = frame[3 * a], y = frame[3 * a + 1], z = frame[3 * a + 2];
-        if (STAGE) { s_xyz[3 * i] = x; s_xyz[3 * i + 1] = y; s_xyz[3 * i + 2] = z; }
-        if (WEIGHTED) {
-            const double wi = w[i];
-            c[0] = fma(wi, (double)x, c[0]); c[1] = fma(wi, (double)y, c[1]); c[2] = fma(wi, (double)z, c[2]);
-            c[3] += wi;
-        } else {
-            c[0] += (double)x; c[1] += (double)y; c[2] += (double)z;
+    // ---- single pass over the fitted atoms ---------------------------------------------
+    double acc[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) acc[k] = 0.0;
+    uint64_t scalar_from = 0;
+    if (VEC) {      // natoms % 4 == 0 and no index list: 16-byte loads, 4 atoms per step
+        const float4 *fr4 = reinterpret_cast<const float4 *>(frame);
+        const double2 *rc2 = reinterpret_cast<const double2 *>(refc);
+        const uint64_t nquad = nsel / 4;
+        scalar_from = nquad * 4;
+#pragma unroll 2
+        for (uint64_t q = threadIdx.x; q < nquad; q += T) {
+            const float4 v0 = fr4[3 * q], v1 = fr4[3 * q + 1], v2 = fr4[3 * q + 2];
+            const double2 r0 = __ldg(rc2 + 6 * q), r1 = __ldg(rc2 + 6 * q + 1), r2 = __ldg(rc2 + 6 * q + 2);
+            const double2 r3 = __ldg(rc2 + 6 * q + 3), r4 = __ldg(rc2 + 6 * q + 4), r5 = __ldg(rc2 + 6 * q + 5);
+            double w0 = 1.0, w1 = 1.0, w2 = 1.0, w3 = 1.0;
+            if (WEIGHTED) {
+                const double2 wa = __ldg(reinterpret_cast<const double2 *>(w) + 2 * q);
+                const double2 wb = __ldg(reinterpret_cast<const double2 *>(w) + 2 * q + 1);
+                w0 = wa.x; w1 = wa.y; w2 = wb.x; w3 = wb.y;
+            }
+            qcp_accumulate<WEIGHTED>(acc, v0.x, v0.y, v0.z, px, py, pz, r0.x, r0.y, r1.x, w0);
+            qcp_accumulate<WEIGHTED>(acc, v0.w, v1.x, v1.y, px, py, pz, r1.y, r2.x, r2.y, w1);
+            qcp_accumulate<WEIGHTED>(acc, v1.z, v1.w, v2.x, px, py, pz, r3.x, r3.y, r4.x, w2);
+            qcp_accumulate<WEIGHTED>(acc, v2.y, v2.z, v2.w, px, py, pz, r4.y, r5.x, r5.y, w3);
         }
     }
-    block_sum<4, QCP_THREADS>(c, scratch);
-    const double wsum = WEIGHTED ? c[3] : (double)nsel;
-    const double mx = c[0] / wsum, my = c[1] / wsum, mz = c[2] / wsum;
+    for (uint64_t i = scalar_from + threadIdx.x; i < nsel; i += T) {
+        const uint64_t a = sel ? (uint64_t)sel[i] : i;
+        const float fx = frame[3 * a], fy = frame[3 * a + 1], fz = frame[3 * a + 2];
+        qcp_accumulate<WEIGHTED>(acc, fx, fy, fz, px, py, pz, refc[3 * i], refc[3 * i + 1], refc[3 * i + 2],
+                                 WEIGHTED ? w[i] : 1.0);
+    }
+    block_sum<13, T>(acc, scratch);
+
+    const double W = refinfo->wsum;                       // sum of weights (nsel when unweighted)
+    const double m0 = acc[10] / W, m1 = acc[11] / W, m2 = acc[12] / W;     // centre relative to the pivot
+    const double mx = px + m0, my = py + m1, mz = pz + m2;
     const double rx = refinfo->com[0], ry = refinfo->com[1], rz = refinfo->com[2];
 
-    // ---- pass 2: inner product of the centred coordinates ---------------------------
-    // M[a][b] = sum w * mobile_a * ref_b ; G1 = sum w |mobile|^2
-    double acc[11];
-#pragma unroll
-    for (int k = 0; k < 11; ++k) acc[k] = 0.0;
-    for (uint64_t i = threadIdx.x; i < nsel; i += QCP_THREADS) {
-        float fx, fy, fz;
-        if (STAGE) { fx = s_xyz[3 * i]; fy = s_xyz[3 * i + 1]; fz = s_xyz[3 * i + 2]; }
-        else {
+    // ---- optional: align.rotation_matrix's allclose early exit ---------------------------
+    double notclose = 0.0;
+    if (allclose_shortcut) {
+        for (uint64_t i = threadIdx.x; i < nsel; i += T) {
             const uint64_t a = sel ? (uint64_t)sel[i] : i;
-            fx = frame[3 * a]; fy = frame[3 * a + 1]; fz = frame[3 * a + 2];
+            const double y0 = (double)frame[3 * a] - mx, y1 = (double)frame[3 * a + 1] - my, y2 = (double)frame[3 * a + 2] - mz;
+            if (!(qcp_close(y0, refc[3 * i]) && qcp_close(y1, refc[3 * i + 1]) && qcp_close(y2, refc[3 * i + 2])))
+                notclose = 1.0;
         }
-        const double y0 = (double)fx - mx, y1 = (double)fy - my, y2 = (double)fz - mz;
-        const double x0 = (double)ref[3 * i] - rx, x1 = (double)ref[3 * i + 1] - ry, x2 = (double)ref[3 * i + 2] - rz;
-        double w0 = y0, w1 = y1, w2 = y2;
-        if (WEIGHTED) { const double wi = w[i]; w0 *= wi; w1 *= wi; w2 *= wi; }
-        acc[0] = fma(w0, x0, acc[0]); acc[1] = fma(w0, x1, acc[1]); acc[2] = fma(w0, x2, acc[2]);
-        acc[3] = fma(w1, x0, acc[3]); acc[4] = fma(w1, x1, acc[4]); acc[5] = fma(w1, x2, acc[5]);
-        acc[6] = fma(w2, x0, acc[6]); acc[7] = fma(w2, x1, acc[7]); acc[8] = fma(w2, x2, acc[8]);
-        acc[9] = fma(w0, y0, fma(w1, y1, fma(w2, y2, acc[9])));
-        if (allclose_shortcut) {
-            // np.allclose(mobile, ref): |a - b| <= 1e-8 + 1e-5 |b|   (align.py:290)
-            const bool ok = fabs(y0 - x0) <= 1e-8 + 1e-5 * fabs(x0) &&
-                            fabs(y1 - x1) <= 1e-8 + 1e-5 * fabs(x1) &&
-                            fabs(y2 - x2) <= 1e-8 + 1e-5 * fabs(x2);
-            if (!ok) acc[10] += 1.0;
-        }
+        notclose = (double)__syncthreads_or(notclose != 0.0);
     }
-    block_sum<11, QCP_THREADS>(acc, scratch);
 
     if (threadIdx.x == 0) {
         double A[9], R[9];
         double rms;
         const bool need_rot = rot_out != nullptr || aligned != nullptr;
-        if (allclose_shortcut && acc[10] == 0.0) {
+        if (allclose_shortcut && notclose == 0.0) {
             rms = 0.0;
             for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
         } else {
+            // M[a][b] = sum w (y_a - y_com_a) (x_b - x_com_b)
+            const double sx[3] = { refinfo->sx[0], refinfo->sx[1], refinfo->sx[2] };
+            const double m[3] = { m0, m1, m2 };
+            double M[9];
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) M[3 * a + b] = acc[3 * a + b] - m[a] * sx[b];
             if (convention == 0) {
-                for (int k = 0; k < 9; ++k) A[k] = acc[k];                 // coords1 = mobile (rms.py:699-701)
+                for (int k = 0; k < 9; ++k) A[k] = M[k];                       // coords1 = mobile (rms.py:699-701)
             } else {
-                for (int a = 0; a < 3; ++a)                                  // coords1 = reference (align.py:306)
-                    for (int b = 0; b < 3; ++b) A[3 * a + b] = acc[3 * b + a];
+                for (int a = 0; a < 3; ++a)                                    // coords1 = reference (align.py:306)
+                    for (int b = 0; b < 3; ++b) A[3 * a + b] = M[3 * b + a];
             }
-            const double E0 = (acc[9] + refinfo->g2) * 0.5;
+            const double G1 = acc[9] - W * (m0 * m0 + m1 * m1 + m2 * m2);
+            const double E0 = (G1 + refinfo->g2) * 0.5;
             rms = qcp_solve(need_rot ? R : nullptr, A, E0, (double)nsel);
         }
         rmsd_out[f] = rms;
@@ -177,32 +234,366 @@ qcp_traj_kernel(const float *traj, uint64_t natoms, const int32_t *__restrict__ 
     if (aligned == nullptr) return;
     __syncthreads();
 
-    // ---- pass 3: move every atom of the frame --------------------------------------
+    // ---- second pass: move every atom of the frame ---------------------------------------
     // translate(-com), rotate, translate(+ref_com): each step computed in float64
     // and stored back as float32 (core/groups.py:1480, 1527; rms.py:705-711).
     double R[9];
+    if (convention == 0) {        // x . R
 #pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = s_rot[k];
+        for (int k = 0; k < 9; ++k) R[k] = s_rot[k];
+    } else {                      // x . R^T
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) R[3 * a + b] = s_rot[3 * b + a];
+    }
     const double cx = s_com[0], cy = s_com[1], cz = s_com[2];
     float *dst = aligned + f * natoms * 3;
-    for (uint64_t a = threadIdx.x; a < natoms; a += QCP_THREADS) {
-        const float p0 = (float)((double)frame[3 * a] - cx);
-        const float p1 = (float)((double)frame[3 * a + 1] - cy);
-        const float p2 = (float)((double)frame[3 * a + 2] - cz);
-        double q0, q1, q2;
-        if (convention == 0) {        // x . R
-            q0 = fma((double)p2, R[6], fma((double)p1, R[3], (double)p0 * R[0]));
-            q1 = fma((double)p2, R[7], fma((double)p1, R[4], (double)p0 * R[1]));
-            q2 = fma((double)p2, R[8], fma((double)p1, R[5], (double)p0 * R[2]));
-        } else {                      // x . R^T
-            q0 = fma((double)p2, R[2], fma((double)p1, R[1], (double)p0 * R[0]));
-            q1 = fma((double)p2, R[5], fma((double)p1, R[4], (double)p0 * R[3]));
-            q2 = fma((double)p2, R[8], fma((double)p1, R[7], (double)p0 * R[6]));
-        }
+    auto move = [&](float x, float y, float z, float &ox, float &oy, float &oz) {
+        const float p0 = (float)((double)x - cx);
+        const float p1 = (float)((double)y - cy);
+        const float p2 = (float)((double)z - cz);
+        const double q0 = fma((double)p2, R[6], fma((double)p1, R[3], (double)p0 * R[0]));
+        const double q1 = fma((double)p2, R[7], fma((double)p1, R[4], (double)p0 * R[1]));
+        const double q2 = fma((double)p2, R[8], fma((double)p1, R[5], (double)p0 * R[2]));
         const float r0 = (float)q0, r1 = (float)q1, r2 = (float)q2;
-        dst[3 * a] = (float)((double)r0 + rx);
-        dst[3 * a + 1] = (float)((double)r1 + ry);
-        dst[3 * a + 2] = (float)((double)r2 + rz);
+        ox = (float)((double)r0 + rx);
+        oy = (float)((double)r1 + ry);
+        oz = (float)((double)r2 + rz);
+    };
+    uint64_t from = 0;
+    if (VEC) {
+        const float4 *fr4 = reinterpret_cast<const float4 *>(frame);
+        float4 *dst4 = reinterpret_cast<float4 *>(dst);
+        const uint64_t nquad = natoms / 4;
+        from = nquad * 4;
+#pragma unroll 2
+        for (uint64_t q = threadIdx.x; q < nquad; q += T) {
+            const float4 v0 = fr4[3 * q], v1 = fr4[3 * q + 1], v2 = fr4[3 * q + 2];
+            float4 o0, o1, o2;
+            move(v0.x, v0.y, v0.z, o0.x, o0.y, o0.z);
+            move(v0.w, v1.x, v1.y, o0.w, o1.x, o1.y);
+            move(v1.z, v1.w, v2.x, o1.z, o1.w, o2.x);
+            move(v2.y, v2.z, v2.w, o2.y, o2.z, o2.w);
+            dst4[3 * q] = o0; dst4[3 * q + 1] = o1; dst4[3 * q + 2] = o2;
+        }
+    }
+    for (uint64_t a = from + threadIdx.x; a < natoms; a += T)
+        move(frame[3 * a], frame[3 * a + 1], frame[3 * a + 2], dst[3 * a], dst[3 * a + 1], dst[3 * a + 2]);
+}
+
+// ---------------------------------------------------------------------------
+// TMA-streamed variant (contiguous selection, 16-byte aligned frames)
+// ---------------------------------------------------------------------------
+// Persistent CTAs, one per SM.  One elected thread streams chunks of QS_CH atoms
+// with cp.async.bulk (1-D TMA) into a 2-3 stage shared-memory ring guarded by
+// full/empty mbarriers; 16 warps in 4 groups of 128 threads work on 4
+// frames at once, so the float64 reference chunk (staged once per stage) is
+// shared by 4 frames and its L2 traffic is a quarter of a frame's HBM traffic.
+// No registers are spent on loads in flight: up to ~144 kB per SM are in flight.
+// With `aligned`, the same ring streams the 4 frames a second time (L2-resident:
+// 148 x 4 frames x 120 kB) and the consumers apply the rigid transform.
+constexpr int QS_CH = 1024;                 // atoms per chunk
+constexpr int QS_FB = 4;                    // frames per batch = consumer groups
+constexpr int QS_GT = 128;                  // threads per group
+constexpr int QS_THREADS = QS_FB * QS_GT;
+constexpr int QS_REF_BYTES = QS_CH * 3 * 8;          // 6 planes x 256 double2
+constexpr int QS_W_BYTES = QS_CH * 8;                // 2 planes x 256 double2
+constexpr int QS_FRAME_BYTES = QS_CH * 12;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void group_sync(int group)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(QS_GT) : "memory");
+}
+
+// float -> double without the (quarter-rate) conversion unit: exact for normal numbers,
+// everything else takes the hardware conversion.
+__device__ __forceinline__ double f2d_alu(float x)
+{
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t e = b & 0x7f800000u;
+    if (e == 0u || e == 0x7f800000u) return (double)x;
+    const uint32_t hi = (b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u);
+    return __hiloint2double((int)hi, (int)(b << 29));
+}
+
+// chunked plane layout of the centred reference: for chunk c, plane p (0..5), quad q (0..255)
+// the double2 {d[2p], d[2p+1]} of the quad's 12 doubles d = {x0 y0 z0 x1 y1 z1 ...};
+// weights: plane p (0..1) holds {w[2p], w[2p+1]} of the quad.  Padding is zero.
+__global__ void __launch_bounds__(256)
+qcp_ref_planes_kernel(const double *__restrict__ refc, const double *__restrict__ w, uint64_t nsel,
+                      uint64_t nchunks, double2 *__restrict__ refp, double2 *__restrict__ wp)
+{
+    const uint64_t total = nchunks * (QS_CH / 4);
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t c = t / (QS_CH / 4), q = t % (QS_CH / 4);
+        double d[12], ww[4];
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t atom = c * QS_CH + q * 4 + k;
+            const bool ok = atom < nsel;
+            for (int j = 0; j < 3; ++j) d[3 * k + j] = ok ? refc[3 * atom + j] : 0.0;
+            ww[k] = ok ? (w ? w[atom] : 1.0) : 0.0;
+        }
+        for (int pl = 0; pl < 6; ++pl) refp[(c * 6 + pl) * (QS_CH / 4) + q] = make_double2(d[2 * pl], d[2 * pl + 1]);
+        if (wp)
+            for (int pl = 0; pl < 2; ++pl) wp[(c * 2 + pl) * (QS_CH / 4) + q] = make_double2(ww[2 * pl], ww[2 * pl + 1]);
+    }
+}
+
+struct QcpStreamParams {
+    const float *traj;
+    uint64_t nframes, natoms, nsel;
+    const double *refc;          // flat centred reference (allclose slow path)
+    const double2 *refp, *wp;    // chunked planes
+    const RefInfo *refinfo;
+    double *rmsd_out, *rot_out;
+    float *aligned;
+    int convention, allclose_shortcut;
+};
+
+template <bool WEIGHTED, int QS_STAGES>
+__global__ void __launch_bounds__(QS_THREADS, 1) qcp_stream_kernel(const QcpStreamParams p)
+{
+    extern __shared__ __align__(128) unsigned char qs_smem[];
+    __shared__ uint64_t full_bar[QS_STAGES], empty_bar[QS_STAGES];
+    __shared__ double red[QS_FB][13 * (QS_GT / 32)];
+    __shared__ double s_xf[QS_FB][12];
+    constexpr int STAGE_BYTES = QS_REF_BYTES + (WEIGHTED ? QS_W_BYTES : 0) + QS_FB * QS_FRAME_BYTES;
+    constexpr int FRAME_OFF = QS_REF_BYTES + (WEIGHTED ? QS_W_BYTES : 0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < QS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], QS_FB * QS_GT / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t nbatch = (p.nframes + QS_FB - 1) / QS_FB;
+    const uint32_t nchA = (uint32_t)((p.nsel + QS_CH - 1) / QS_CH);
+    const uint32_t nchB = p.aligned ? (uint32_t)((p.natoms + QS_CH - 1) / QS_CH) : 0u;
+
+    // ---------------- producer role (lane 0 of warp 0) ----------------
+    // Chunk number `k` of this CTA (over all its batches and both passes) goes to stage k % STAGES.
+    const uint32_t per_batch = nchA + nchB;
+    const uint64_t my_batches = nbatch > blockIdx.x ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint64_t my_chunks = my_batches * per_batch;
+    auto issue = [&](uint64_t k) {
+        const uint64_t b = blockIdx.x + (k / per_batch) * gridDim.x;
+        const uint32_t c = (uint32_t)(k % per_batch);
+        const uint64_t f0 = b * QS_FB;
+        const int nf = (int)min((uint64_t)QS_FB, p.nframes - f0);
+        const int s = (int)(k % QS_STAGES);
+        unsigned char *st = qs_smem + (size_t)s * STAGE_BYTES;
+        const bool passA = c < nchA;
+        const uint32_t cc = passA ? c : c - nchA;
+        const uint64_t lim = passA ? p.nsel : p.natoms;
+        const uint32_t na = (uint32_t)min((uint64_t)QS_CH, lim - (uint64_t)cc * QS_CH);
+        const uint32_t fbytes = ((na + 3u) & ~3u) * 12u;
+        uint32_t bytes = (uint32_t)nf * fbytes;
+        if (passA) bytes += QS_REF_BYTES + (WEIGHTED ? QS_W_BYTES : 0);
+        mbar_expect_tx(&full_bar[s], bytes);
+        if (passA) {
+            bulk_g2s(st, p.refp + (uint64_t)cc * 6 * (QS_CH / 4), QS_REF_BYTES, &full_bar[s]);
+            if (WEIGHTED) bulk_g2s(st + QS_REF_BYTES, p.wp + (uint64_t)cc * 2 * (QS_CH / 4), QS_W_BYTES, &full_bar[s]);
+        }
+        for (int g = 0; g < nf; ++g)
+            bulk_g2s(st + FRAME_OFF + g * QS_FRAME_BYTES, p.traj + ((f0 + g) * p.natoms + (uint64_t)cc * QS_CH) * 3,
+                     fbytes, &full_bar[s]);
+    };
+    // after every consumed chunk: warp 0 waits until all warps have released the stage, then refills it
+    auto release_and_refill = [&](uint32_t k) {
+        __syncwarp();
+        if (lane == 0) {
+            const int s = k % QS_STAGES;
+            mbar_arrive(&empty_bar[s]);
+            if (warp == 0 && (uint64_t)k + QS_STAGES < my_chunks) {
+                mbar_wait(&empty_bar[s], (k / QS_STAGES) & 1u);
+                issue((uint64_t)k + QS_STAGES);
+            }
+        }
+    };
+    if (tid == 0)
+        for (uint64_t k = 0; k < QS_STAGES && k < my_chunks; ++k) issue(k);
+
+    // ---------------- consumers ----------------
+    const int g = warp / (QS_GT / 32), gt = tid % QS_GT;
+    const double W = p.refinfo->wsum;
+    const double rx = p.refinfo->com[0], ry = p.refinfo->com[1], rz = p.refinfo->com[2];
+    uint32_t it = 0;
+    for (uint64_t b = blockIdx.x; b < nbatch; b += gridDim.x) {
+        const uint64_t f = b * QS_FB + g;
+        const bool active = f < p.nframes;
+        double acc[13];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) acc[k] = 0.0;
+        double px = 0.0, py = 0.0, pz = 0.0;
+        for (uint32_t c = 0; c < nchA; ++c, ++it) {
+            const int s = it % QS_STAGES;
+            mbar_wait(&full_bar[s], (it / QS_STAGES) & 1u);
+            if (active) {
+                const unsigned char *st = qs_smem + (size_t)s * STAGE_BYTES;
+                const double2 *rp = reinterpret_cast<const double2 *>(st);
+                const double2 *wq = reinterpret_cast<const double2 *>(st + QS_REF_BYTES);
+                const float4 *fr4 = reinterpret_cast<const float4 *>(st + FRAME_OFF + g * QS_FRAME_BYTES);
+                if (c == 0) {
+                    const float4 first = fr4[0];
+                    px = (double)first.x; py = (double)first.y; pz = (double)first.z;
+                }
+                const uint32_t na = (uint32_t)min((uint64_t)QS_CH, p.nsel - (uint64_t)c * QS_CH);
+#pragma unroll
+                for (int h = 0; h < QS_CH / 4 / QS_GT; ++h) {
+                    const uint32_t q = gt + h * QS_GT;
+                    if (q * 4 >= na) break;
+                    float4 v0 = fr4[3 * q], v1 = fr4[3 * q + 1], v2 = fr4[3 * q + 2];
+                    if (q * 4 + 4 > na) {       // ragged last quad: atoms past the selection count as the pivot (zero y')
+                        const float fx = (float)px, fy = (float)py, fz = (float)pz;
+                        if (q * 4 + 1 >= na) { v0.w = fx; v1.x = fy; v1.y = fz; }
+                        if (q * 4 + 2 >= na) { v1.z = fx; v1.w = fy; v2.x = fz; }
+                        if (q * 4 + 3 >= na) { v2.y = fx; v2.z = fy; v2.w = fz; }
+                    }
+                    const double2 r0 = rp[q], r1 = rp[QS_CH / 4 + q], r2 = rp[2 * (QS_CH / 4) + q];
+                    const double2 r3 = rp[3 * (QS_CH / 4) + q], r4 = rp[4 * (QS_CH / 4) + q], r5 = rp[5 * (QS_CH / 4) + q];
+                    double w0 = 1.0, w1 = 1.0, w2 = 1.0, w3 = 1.0;
+                    if (WEIGHTED) {
+                        const double2 wa = wq[q], wb = wq[QS_CH / 4 + q];
+                        w0 = wa.x; w1 = wa.y; w2 = wb.x; w3 = wb.y;
+                    }
+                    qcp_accumulate<WEIGHTED>(acc, v0.x, v0.y, v0.z, px, py, pz, r0.x, r0.y, r1.x, w0);
+                    qcp_accumulate<WEIGHTED>(acc, v0.w, v1.x, v1.y, px, py, pz, r1.y, r2.x, r2.y, w1);
+                    qcp_accumulate<WEIGHTED>(acc, v1.z, v1.w, v2.x, px, py, pz, r3.x, r3.y, r4.x, w2);
+                    qcp_accumulate<WEIGHTED>(acc, v2.y, v2.z, v2.w, px, py, pz, r4.y, r5.x, r5.y, w3);
+                }
+            }
+            release_and_refill(it);
+        }
+        // ---- group reduction (4 warps) and solve ------------------------------------------
+        {
+            const int gw = (tid % QS_GT) >> 5;
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {
+                const double v = warp_sum(acc[k]);
+                if (lane == 0) red[g][k * (QS_GT / 32) + gw] = v;
+            }
+            group_sync(g);
+            if (gt == 0 && active) {
+                double sum[13];
+                for (int k = 0; k < 13; ++k) {
+                    double v = 0.0;
+                    for (int w4 = 0; w4 < QS_GT / 32; ++w4) v += red[g][k * (QS_GT / 32) + w4];
+                    sum[k] = v;
+                }
+                const double m0 = sum[10] / W, m1 = sum[11] / W, m2 = sum[12] / W;
+                const double mx = px + m0, my = py + m1, mz = pz + m2;
+                const double sx[3] = { p.refinfo->sx[0], p.refinfo->sx[1], p.refinfo->sx[2] };
+                const double m[3] = { m0, m1, m2 };
+                double M[9], A[9], R[9];
+                for (int a = 0; a < 3; ++a)
+                    for (int bb = 0; bb < 3; ++bb) M[3 * a + bb] = sum[3 * a + bb] - m[a] * sx[bb];
+                const double G1 = sum[9] - W * (m0 * m0 + m1 * m1 + m2 * m2);
+                const bool need_rot = p.rot_out != nullptr || p.aligned != nullptr;
+                bool close = false;
+                if (p.allclose_shortcut) {
+                    // np.allclose(mobile, ref) implies sum |a - b|^2 <= close_sum; only then look elementwise
+                    const double d2 = G1 + p.refinfo->g2 - 2.0 * (M[0] + M[4] + M[8]);
+                    if (d2 <= p.refinfo->close_sum * 1.001 + 1e-9 * (G1 + p.refinfo->g2)) {
+                        close = true;
+                        const float *frame = p.traj + f * p.natoms * 3;
+                        for (uint64_t i = 0; i < p.nsel && close; ++i)
+                            close = qcp_close((double)frame[3 * i] - mx, p.refc[3 * i]) &&
+                                    qcp_close((double)frame[3 * i + 1] - my, p.refc[3 * i + 1]) &&
+                                    qcp_close((double)frame[3 * i + 2] - mz, p.refc[3 * i + 2]);
+                    }
+                }
+                double rms;
+                if (close) {
+                    rms = 0.0;
+                    for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+                } else {
+                    if (p.convention == 0) {
+                        for (int k = 0; k < 9; ++k) A[k] = M[k];
+                    } else {
+                        for (int a = 0; a < 3; ++a)
+                            for (int bb = 0; bb < 3; ++bb) A[3 * a + bb] = M[3 * bb + a];
+                    }
+                    rms = qcp_solve(need_rot ? R : nullptr, A, (G1 + p.refinfo->g2) * 0.5, (double)p.nsel);
+                }
+                p.rmsd_out[f] = rms;
+                if (p.rot_out)
+                    for (int k = 0; k < 9; ++k) p.rot_out[f * 9 + k] = R[k];
+                if (p.aligned) {
+                    for (int a = 0; a < 3; ++a)
+                        for (int bb = 0; bb < 3; ++bb)
+                            s_xf[g][3 * a + bb] = p.convention == 0 ? R[3 * a + bb] : R[3 * bb + a];   // x.R or x.R^T
+                    s_xf[g][9] = mx; s_xf[g][10] = my; s_xf[g][11] = mz;
+                }
+            }
+            group_sync(g);        // red[] reusable, s_xf visible
+        }
+        if (nchB == 0) continue;
+        // ---- second pass: rigid transform of every atom (core/groups.py:1480, 1527) --------
+        double R[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = s_xf[g][k];
+        const double cx = s_xf[g][9], cy = s_xf[g][10], cz = s_xf[g][11];
+        auto move = [&](float x, float y, float z, float &ox, float &oy, float &oz) {
+            const float p0 = (float)(f2d_alu(x) - cx);
+            const float p1 = (float)(f2d_alu(y) - cy);
+            const float p2 = (float)(f2d_alu(z) - cz);
+            const double d0 = f2d_alu(p0), d1 = f2d_alu(p1), d2 = f2d_alu(p2);
+            const float r0 = (float)fma(d2, R[6], fma(d1, R[3], d0 * R[0]));
+            const float r1 = (float)fma(d2, R[7], fma(d1, R[4], d0 * R[1]));
+            const float r2 = (float)fma(d2, R[8], fma(d1, R[5], d0 * R[2]));
+            ox = (float)(f2d_alu(r0) + rx);
+            oy = (float)(f2d_alu(r1) + ry);
+            oz = (float)(f2d_alu(r2) + rz);
+        };
+        for (uint32_t c = 0; c < nchB; ++c, ++it) {
+            const int s = it % QS_STAGES;
+            mbar_wait(&full_bar[s], (it / QS_STAGES) & 1u);
+            if (active) {
+                const unsigned char *st = qs_smem + (size_t)s * STAGE_BYTES;
+                const float4 *fr4 = reinterpret_cast<const float4 *>(st + FRAME_OFF + g * QS_FRAME_BYTES);
+                float4 *dst4 = reinterpret_cast<float4 *>(p.aligned + (f * p.natoms + (uint64_t)c * QS_CH) * 3);
+                const uint32_t na = (uint32_t)min((uint64_t)QS_CH, p.natoms - (uint64_t)c * QS_CH);   // multiple of 4
+#pragma unroll
+                for (int h = 0; h < QS_CH / 4 / QS_GT; ++h) {
+                    const uint32_t q = gt + h * QS_GT;
+                    if (q * 4 >= na) break;
+                    const float4 v0 = fr4[3 * q], v1 = fr4[3 * q + 1], v2 = fr4[3 * q + 2];
+                    float4 o0, o1, o2;
+                    move(v0.x, v0.y, v0.z, o0.x, o0.y, o0.z);
+                    move(v0.w, v1.x, v1.y, o0.w, o1.x, o1.y);
+                    move(v1.z, v1.w, v2.x, o1.z, o1.w, o2.x);
+                    move(v2.y, v2.z, v2.w, o2.y, o2.z, o2.w);
+                    dst4[3 * q] = o0; dst4[3 * q + 1] = o1; dst4[3 * q + 2] = o2;
+                }
+            }
+            release_and_refill(it);
+        }
     }
 }
 
@@ -292,29 +683,63 @@ extern "C" int mdagpu_qcp_trajectory(const float *traj, uint64_t nframes, uint64
     MDA_CUDA(w.init(weights, nsel * sizeof(double), space, st));
     MDA_CUDA(rm.init(rmsd, nframes * sizeof(double), space, st));
     MDA_CUDA(ro.init(rot, nframes * 9 * sizeof(double), space, st));
-    DevBuf info;
+    DevBuf info, refc;
     MDA_CUDA(info.alloc(sizeof(RefInfo), st));
+    MDA_CUDA(refc.alloc(nsel * 3 * sizeof(double), st));
     const double *wd = weights ? w.as<double>() : nullptr;
     const int32_t *sd = sel ? s.as<int32_t>() : nullptr;
-    MDA_LAUNCH(qcp_ref_kernel, 1, QCP_THREADS, 0, st, r.as<float>(), wd, nsel, info.as<RefInfo>());
+    MDA_LAUNCH(qcp_ref_kernel, 1, QCP_THREADS, 0, st, r.as<float>(), wd, nsel, info.as<RefInfo>(), refc.as<double>());
     MDA_CHECK_LAUNCH();
 
-    const size_t stage_bytes = nsel * 3 * sizeof(float);
-    const bool stage = stage_bytes <= 200 * 1024;
-    const size_t smem = stage ? stage_bytes : 0;
-#define QCP_LAUNCH(W, S)                                                                         \
-    do {                                                                                         \
-        auto kern = qcp_traj_kernel<W, S>;                                                       \
-        if (smem > 48 * 1024)                                                                    \
-            MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        MDA_LAUNCH_AS("qcp_traj_kernel", kern, (unsigned)nframes, QCP_THREADS, smem, st, t.as<float>(), natoms, sd, nsel, \
-                   r.as<float>(), wd, info.as<RefInfo>(), rm.as<double>(),                       \
-                   rot ? ro.as<double>() : nullptr, aligned ? al.as<float>() : nullptr,          \
-                   convention, allclose_shortcut);                                               \
-    } while (0)
+    // 16-byte path: every frame starts on a 16-byte boundary and the fitted atoms are a prefix
+    const bool vec = sel == nullptr && natoms % 4 == 0 && ((uintptr_t)t.dev % 16 == 0) &&
+                     (!aligned || (uintptr_t)al.dev % 16 == 0) && (!weights || (uintptr_t)wd % 16 == 0);
     MDA_REQUIRE(nframes <= 0x7fffffffull, "mdagpu_qcp_trajectory: too many frames in one call");
-    if (weights) { if (stage) QCP_LAUNCH(true, true); else QCP_LAUNCH(true, false); }
-    else { if (stage) QCP_LAUNCH(false, true); else QCP_LAUNCH(false, false); }
+    if (vec && nsel >= 2048) {
+        // TMA-streamed persistent kernel
+        const uint64_t nch = (nsel + QS_CH - 1) / QS_CH;
+        DevBuf refp, wp;
+        MDA_CUDA(refp.alloc(nch * QS_REF_BYTES, st));
+        if (weights) MDA_CUDA(wp.alloc(nch * QS_W_BYTES, st));
+        MDA_LAUNCH(qcp_ref_planes_kernel, cdiv(nch * (QS_CH / 4), 256), 256, 0, st, refc.as<double>(), wd, nsel, nch,
+                   refp.as<double2>(), weights ? wp.as<double2>() : nullptr);
+        MDA_CHECK_LAUNCH();
+        QcpStreamParams qp;
+        qp.traj = t.as<float>(); qp.nframes = nframes; qp.natoms = natoms; qp.nsel = nsel;
+        qp.refc = refc.as<double>(); qp.refp = refp.as<double2>(); qp.wp = weights ? wp.as<double2>() : nullptr;
+        qp.refinfo = info.as<RefInfo>(); qp.rmsd_out = rm.as<double>(); qp.rot_out = rot ? ro.as<double>() : nullptr;
+        qp.aligned = aligned ? al.as<float>() : nullptr; qp.convention = convention; qp.allclose_shortcut = allclose_shortcut;
+        const uint64_t nbatch = (nframes + QS_FB - 1) / QS_FB;
+        const unsigned grid = (unsigned)(nbatch < (uint64_t)num_sms() ? nbatch : (uint64_t)num_sms());
+        // ring depth: as many stages as fit in the 227 kB of one SM (3 x 72 kB, or 2 x 80 kB with weights)
+        if (weights) {
+            const size_t smem = 2 * (size_t)(QS_REF_BYTES + QS_W_BYTES + QS_FB * QS_FRAME_BYTES);
+            MDA_CUDA(cudaFuncSetAttribute(qcp_stream_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<true, 2>), grid, QS_THREADS, smem, st, qp);
+        } else {
+            const size_t smem = 3 * (size_t)(QS_REF_BYTES + QS_FB * QS_FRAME_BYTES);
+            MDA_CUDA(cudaFuncSetAttribute(qcp_stream_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<false, 3>), grid, QS_THREADS, smem, st, qp);
+        }
+        MDA_CHECK_LAUNCH();
+        MDA_CUDA(rm.finish());
+        if (rot) MDA_CUDA(ro.finish());
+        if (aligned) MDA_CUDA(al.finish());
+        return MDAGPU_OK;
+    }
+#define QCP_LAUNCH(T, W, V)                                                                      \
+    MDA_LAUNCH_AS("qcp_traj_kernel", (qcp_traj_kernel<T, W, V>), (unsigned)nframes, T, 0, st, t.as<float>(), natoms, sd, nsel, \
+                  refc.as<double>(), wd, info.as<RefInfo>(), rm.as<double>(),                    \
+                  rot ? ro.as<double>() : nullptr, aligned ? al.as<float>() : nullptr,           \
+                  convention, allclose_shortcut)
+    // small selections: one warp-sized CTA would idle most lanes in the reduction; large: 256 threads
+    if (nsel >= 2048) {
+        if (weights) { if (vec) QCP_LAUNCH(256, true, true); else QCP_LAUNCH(256, true, false); }
+        else { if (vec) QCP_LAUNCH(256, false, true); else QCP_LAUNCH(256, false, false); }
+    } else {
+        if (weights) { if (vec) QCP_LAUNCH(64, true, true); else QCP_LAUNCH(64, true, false); }
+        else { if (vec) QCP_LAUNCH(64, false, true); else QCP_LAUNCH(64, false, false); }
+    }
 #undef QCP_LAUNCH
     MDA_CHECK_LAUNCH();
     MDA_CUDA(rm.finish());

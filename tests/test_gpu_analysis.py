@@ -230,3 +230,33 @@ def test_self_contacts(oracle):
     c2 = self_contacts(torch.as_tensor(pos).cuda(), 8.0)
     assert np.array_equal(c2.cpu().numpy().astype(np.uint64), self_contacts(pos, 8.0))
     assert contact_matrix(np.array([1.0, 8.0, 8.1]), 8.0).tolist() == [True, True, False]
+
+
+@pytest.mark.parametrize("n,F", [(2048, 5), (4100, 9), (10000, 3)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_qcp_trajectory_streamed_kernel(oracle, n, F, weighted):
+    """natoms % 4 == 0 and >= 2048 fitted atoms: the TMA-streamed persistent kernel (qcp.cu,
+    qcp_stream_kernel), incl. ragged last chunk, partial last batch of 4 frames, in-place alignment."""
+    import torch
+    from mdanalysis_b200.lib import qcprot
+    rng = np.random.default_rng(n + F)
+    ref, traj = make_traj(rng, F, n)
+    traj[-1] = ref                                       # np.allclose early exit of rotation_matrix (unweighted)
+    w = rng.uniform(1, 32, n) if weighted else None
+    wn = None if w is None else w / w.mean()
+    want = oracle.rmsd_trajectory(traj, ref, weights=w)
+    for dev in (False, True):
+        t = torch.as_tensor(traj).cuda() if dev else traj
+        vals, rot, _ = qcprot.qcp_trajectory(t, ref, weights=wn, want_rotation=True)
+        vals = vals.cpu().numpy() if dev else vals
+        assert np.allclose(vals[:-1], want[:-1], rtol=1e-9, atol=0)
+        assert abs(vals[-1] - want[-1]) < 1e-5             # identical structures: cancellation noise only
+    moved_want, rm_want = oracle.align_trajectory(traj, ref, weights=w)
+    t = traj.copy()
+    vals, _, moved = qcprot.qcp_trajectory(t, ref, weights=wn, align=True, convention=1,
+                                           allclose_shortcut=not weighted, out=t)
+    assert moved is t
+    assert np.allclose(vals[:-1], rm_want[:-1], rtol=1e-9, atol=0)
+    assert np.abs(t - moved_want).max() <= 8e-6
+    if not weighted:
+        assert vals[-1] == 0.0 and rm_want[-1] == 0.0      # the shortcut fired on both sides
