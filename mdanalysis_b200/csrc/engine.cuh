@@ -49,7 +49,8 @@ struct FrameGeom {
 // given (lib.distances ortho flavour works on unwrapped input).
 __global__ void cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
                                 const FrameGeom *__restrict__ fg, int per_frame, int wrap,
-                                uint32_t *__restrict__ keys, uint32_t *__restrict__ counts);
+                                uint32_t *__restrict__ keys, uint32_t *__restrict__ counts,
+                                unsigned *__restrict__ flag);
 // exclusive scan of counts[0..n) into starts[0..n], starts[n] = total (single CTA, chunked)
 __global__ void exclusive_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ starts,
                                       uint64_t n);
@@ -62,8 +63,10 @@ __global__ void cell_scatter_kernel(const float *__restrict__ xyz, uint64_t n, u
                                     uint32_t *__restrict__ sorted_key);
 
 struct CellList {
-    DevBuf keys, counts, starts, cursor, sorted, sorted_key;
+    DevBuf keys, counts, starts, cursor, sorted, sorted_key, flag;
     uint64_t n = 0, nframes = 0, total_cells = 0;
+    // non-zero when some atom was folded into a cell it does not lie in (see cell_of_checked)
+    const unsigned *inconsistent() const { return flag.as<unsigned>(); }
     const float4 *atoms() const { return sorted.as<float4>(); }
     const uint32_t *start() const { return starts.as<uint32_t>(); }
     const uint32_t *key_of_sorted() const { return sorted_key.as<uint32_t>(); }

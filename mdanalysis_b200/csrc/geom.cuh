@@ -418,6 +418,26 @@ MDA_HD void cell_of(const GridGeom &g, float x, float y, float z, int *c)
     c[2] %= g.ncells[2];
 }
 
+// Same cell as cell_of(); returns false when the C remainder had to fold an index back
+// into range (a coordinate that the float64 cell arithmetic puts outside the wrapped
+// cell, e.g. on the upper face of a triclinic cell): such an atom lives in a cell that
+// is not where it is in space, which the per-cell image prediction of rowtile.cuh
+// cannot handle (the reference's per-pair minimum image can).
+MDA_HD bool cell_of_checked(const GridGeom &g, float x, float y, float z, int *c)
+{
+    const double dx = (double)x - g.origin[0], dy = (double)y - g.origin[1], dz = (double)z - g.origin[2];
+    c[2] = (int)(dz / g.cs[8]);
+    c[1] = (int)((dy - dz * g.cs[7]) / g.cs[4]);
+    c[0] = (int)((dx - dy * g.cs[3] - dz * g.cs[6]) / g.cs[0]);
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (c[k] < 0 || c[k] >= g.ncells[k]) ok = false;
+        c[k] %= g.ncells[k];
+    }
+    return ok;
+}
+
 MDA_HD int64_t cell_linear(const GridGeom &g, const int *c)
 {
     return (int64_t)c[0] + (int64_t)c[1] * g.ncells[0] + (int64_t)c[2] * g.ncells[0] * g.ncells[1];

@@ -85,7 +85,7 @@ void grid_geometry_single(GridGeom *g)
 __global__ void __launch_bounds__(256)
 cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
                 const FrameGeom *__restrict__ fgs, int per_frame, int wrap,
-                uint32_t *__restrict__ keys, uint32_t *__restrict__ counts)
+                uint32_t *__restrict__ keys, uint32_t *__restrict__ counts, unsigned *__restrict__ flag)
 {
     const uint64_t total = n * nframes;
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,7 +98,7 @@ cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
         int64_t cell = 0;
         if (fg.grid.ncell_total > 1) {
             int c[3];
-            cell_of(fg.grid, x, y, z, c);
+            if (!cell_of_checked(fg.grid, x, y, z, c)) atomicOr(flag, 1u);
             // the reference's C remainder can only leave [0,ncells) for positions
             // outside the cell; clamp so that a bad input cannot corrupt memory
             for (int k = 0; k < 3; ++k) c[k] = c[k] < 0 ? 0 : c[k];
@@ -188,6 +188,8 @@ int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameG
     MDA_CUDA(cl->cursor.alloc(total_cells * sizeof(uint32_t), st));
     MDA_CUDA(cl->sorted.alloc(total * sizeof(float4), st));
     MDA_CUDA(cl->sorted_key.alloc(total * sizeof(uint32_t), st));
+    MDA_CUDA(cl->flag.alloc(sizeof(unsigned), st));
+    MDA_CUDA(cudaMemsetAsync(cl->flag.p, 0, sizeof(unsigned), st));
     MDA_CUDA(cudaMemsetAsync(cl->counts.p, 0, total_cells * sizeof(uint32_t), st));
     MDA_CUDA(cudaMemsetAsync(cl->cursor.p, 0, total_cells * sizeof(uint32_t), st));
     if (total == 0) {
@@ -198,7 +200,7 @@ int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameG
     const unsigned cap = (unsigned)num_sms() * 16;
     if (grid > cap) grid = cap;
     MDA_LAUNCH(cell_key_kernel, grid, 256, 0, st, xyz, n, nframes, fg_dev, per_frame, wrap,
-               cl->keys.as<uint32_t>(), cl->counts.as<uint32_t>());
+               cl->keys.as<uint32_t>(), cl->counts.as<uint32_t>(), cl->flag.as<unsigned>());
     MDA_CHECK_LAUNCH();
     MDA_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, st, cl->counts.as<uint32_t>(),
                cl->starts.as<uint32_t>(), total_cells);

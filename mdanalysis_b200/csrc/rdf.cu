@@ -4,14 +4,16 @@
 // np.histogram per frame), analysis/contacts.py:315-338 and
 // analysis/distances.py:102-108 (contact predicate d <= radius).
 //
-// Histogram design: every thread owns a private column of 16-bit counters in
-// shared memory (two bins per 32-bit word, word index = bin/2 * THREADS + tid,
-// so a warp always touches 32 distinct banks and no atomics are needed); a
-// counter that is about to wrap is flushed to the global 64-bit bin with one
-// atomic.  At the end of the CTA the columns are summed with a skewed,
-// conflict-free walk and merged into the global histogram with one 64-bit
-// atomic per non-empty bin.
-#include "engine.cuh"
+// Histogram design: every warp owns a private 32-bit histogram in shared memory
+// (nbins words per warp) that is updated with shared-memory atomics (ATOMS.ADD, one
+// instruction per candidate step, predicated on the lanes that hit); lanes of one
+// warp only collide when they fall into the same bin in the same step.  At the end
+// of the CTA the warp histograms are summed and merged into the global 64-bit
+// histogram with one atomic per non-empty bin.  The FP32 binning uses no
+// conversion-unit instruction: floor() is a magic-number add (the XU pipe runs at
+// 16 lanes/clk/SM on B200, profiles/microbench/pipes_b200.txt, and is kept for
+// the one MUFU.RSQ per step).
+#include "rowtile.cuh"
 
 #include <math.h>
 #include <vector>
@@ -55,32 +57,21 @@ struct HistSink {
     const double *thr;            // [nbins+1] exact thresholds on d2 (device)
     unsigned long long *counts;   // [nbins] global histogram
     int nbins, excl_a, excl_b;
-    float lo, inv_dr, band, d2_fast_max;
+    float c0, inv_dr, band_lim, d2_fast_max;     // c0 = -lo*inv_dr - 0.5, band_lim = 0.5 - band
 
-    __device__ __forceinline__ uint32_t *column() const
+    __device__ __forceinline__ uint32_t *mine() const
     {
         extern __shared__ uint32_t s_hist[];
-        return s_hist + threadIdx.x;
+        return s_hist + (threadIdx.x >> 5) * nbins;
     }
     __device__ __forceinline__ void begin()
     {
         extern __shared__ uint32_t s_hist[];
-        const int nwords = (nbins + 1) >> 1;
-        for (int w = threadIdx.x; w < nwords * T; w += T) s_hist[w] = 0u;
+        for (int w = threadIdx.x; w < nbins * (T / 32); w += T) s_hist[w] = 0u;
     }
-    __device__ __forceinline__ void add(int k, uint32_t weight = 1u)
+    __device__ __forceinline__ bool excluded(int i, int j) const
     {
-        uint32_t *w = column() + (k >> 1) * T;
-        const uint32_t sh = (uint32_t)(k & 1) << 4;
-        uint32_t v = *w;
-        const uint32_t cur = (v >> sh) & 0xffffu;
-        if (cur + weight > 0xffffu) {            // would wrap: flush this counter
-            atomicAdd(&counts[k], (unsigned long long)(cur + weight));
-            v &= ~(0xffffu << sh);
-        } else {
-            v += weight << sh;
-        }
-        *w = v;
+        return excl_a > 0 && (i / excl_a) == (j / excl_b);   // rdf.py:274-278
     }
     // an unordered pair seen once stands for (i,j) and (j,i)
     template <bool SYM> __device__ __forceinline__ uint32_t weight_of(int i, int j) const
@@ -89,67 +80,48 @@ struct HistSink {
         if (i == j) return excluded(i, i) ? 0u : 1u;
         return (excluded(i, j) ? 0u : 1u) + (excluded(j, i) ? 0u : 1u);
     }
+    // FP32 binning: accepted only when the estimate is safely inside a bin and safely
+    // inside the cutoff; everything near a decision boundary goes to hit_w().
+    // floor(u) = round_to_nearest(u - 0.5) by the 2^23 trick; |u - 0.5 - k| < 0.5 - band
+    // <=> frac(u) in (band, 1 - band).  d2f == 0 sits on an edge and falls through.
     template <bool SYM> __device__ __forceinline__ bool try_fast_w(int i, int j, float d2f)
     {
-        if (!(d2f < d2_fast_max)) return false;
-        const float u = (sqrtf(d2f) - lo) * inv_dr;
-        const float fk = floorf(u);
-        const float frac = u - fk;
-        if (!(frac > band && frac < 1.0f - band) || !(u > 0.0f) || !(fk < (float)nbins)) return false;
-        const uint32_t wgt = weight_of<SYM>(i, j);
-        if (wgt) add((int)fk, wgt);
+        float d;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2f));
+        const float u = fmaf(d, inv_dr, c0);
+        const float t = u + 8388608.0f;
+        const float fr = u - (t - 8388608.0f);
+        const int k = __float_as_int(t) - 0x4B000000;
+        if (!(d2f < d2_fast_max && fabsf(fr) < band_lim && (unsigned)k < (unsigned)nbins)) return false;
+        uint32_t wgt = SYM ? 2u : 1u;
+        if (excl_a > 0) {
+            wgt = weight_of<SYM>(i, j);
+            if (!wgt) return true;
+        }
+        atomicAdd(mine() + k, wgt);
         return true;
     }
+    __device__ __forceinline__ bool try_fast(int i, int j, float d2f) { return try_fast_w<false>(i, j, d2f); }
     template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t)
     {
         const uint32_t wgt = weight_of<SYM>(i, j);
         if (!wgt) return;
-        if (!(d2 >= thr[0]) || !(d2 <= thr[nbins])) return;
-        int k = (int)((sqrtf((float)d2) - lo) * inv_dr);
-        k = k < 0 ? 0 : (k > nbins - 1 ? nbins - 1 : k);
-        while (k > 0 && d2 < thr[k]) --k;
-        while (k < nbins - 1 && d2 >= thr[k + 1]) ++k;
-        add(k, wgt);
-    }
-    __device__ __forceinline__ bool excluded(int i, int j) const
-    {
-        return excl_a > 0 && (i / excl_a) == (j / excl_b);   // rdf.py:274-278
-    }
-    // FP32 binning: accepted only when the estimate is safely inside a bin and
-    // safely inside the cutoff; everything near a decision boundary goes to hit().
-    __device__ __forceinline__ bool try_fast(int i, int j, float d2f)
-    {
-        if (!(d2f < d2_fast_max)) return false;
-        const float u = (sqrtf(d2f) - lo) * inv_dr;
-        const float fk = floorf(u);
-        const float frac = u - fk;
-        if (!(frac > band && frac < 1.0f - band) || !(u > 0.0f) || !(fk < (float)nbins)) return false;
-        if (!excluded(i, j)) add((int)fk);
-        return true;
-    }
-    __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t)
-    {
-        if (excluded(i, j)) return;
         if (!(d2 >= thr[0]) || !(d2 <= thr[nbins])) return;     // np.histogram keeps lo <= d <= hi
-        int k = (int)((sqrtf((float)d2) - lo) * inv_dr);
+        int k = (int)(fmaf(sqrtf((float)d2), inv_dr, c0) + 0.5f);
         k = k < 0 ? 0 : (k > nbins - 1 ? nbins - 1 : k);
         while (k > 0 && d2 < thr[k]) --k;
         while (k < nbins - 1 && d2 >= thr[k + 1]) ++k;
-        add(k);
+        atomicAdd(mine() + k, wgt);
     }
+    __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t f) { hit_w<false>(i, j, d2, f); }
     __device__ __forceinline__ void end()
     {
         extern __shared__ uint32_t s_hist[];
         __syncthreads();
         for (int k = threadIdx.x; k < nbins; k += T) {
-            const uint32_t *row = s_hist + (k >> 1) * T;
-            const uint32_t sh = (uint32_t)(k & 1) << 4;
             unsigned long long sum = 0;
-            for (int u = 0; u < T; ++u) {
-                int c = u + (int)threadIdx.x;
-                if (c >= T) c -= T;                       // skewed walk: 32 distinct banks per warp
-                sum += (row[c] >> sh) & 0xffffu;
-            }
+#pragma unroll
+            for (int w = 0; w < T / 32; ++w) sum += s_hist[w * nbins + k];
             if (sum) atomicAdd(&counts[k], sum);
         }
     }
@@ -162,7 +134,7 @@ struct HistSinkGlobal {
     const double *thr;
     unsigned long long *counts;
     int nbins, excl_a, excl_b;
-    float lo, inv_dr, band, d2_fast_max;
+    float lo, inv_dr;
     __device__ __forceinline__ bool try_fast(int, int, float) { return false; }
     template <bool SYM> __device__ __forceinline__ bool try_fast_w(int, int, float) { return false; }
     __device__ __forceinline__ void begin() {}
@@ -215,31 +187,46 @@ struct CountSink {
     }
 };
 
+// How one chunk of frames is traversed.
+struct Traversal {
+    int row;            // 1: row_tile_kernel (rowtile.cuh), 0: cell_tile_kernel (engine.cuh)
+    RowParams rp;
+    uint64_t grid_x;
+    int chunks;
+};
+
 template <int MIC, bool SELF, class Sink>
 static int launch_hist(const CellList &ql, const CellList &cl, const FrameGeom *fg_dev, int per_frame,
-                       uint64_t nframes, uint64_t grid_x, int chunks, const SearchParams &sp,
+                       uint64_t nframes, const Traversal &tv, const SearchParams &sp,
                        const Sink &sink, size_t smem, cudaStream_t st)
 {
-    auto kern = cell_tile_kernel<MIC, SELF, Sink>;
-    if (smem > 32 * 1024)
-        MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)grid_x, (unsigned)nframes);
-    MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, smem, st, ql.atoms(), ql.start(),
-                  cl.atoms(), cl.start(), fg_dev, per_frame, chunks, sp, sink);
+    dim3 grid((unsigned)tv.grid_x, (unsigned)nframes);
+    if (tv.row) {
+        auto kern = row_tile_kernel<MIC, SELF, Sink>;
+        if (smem > 24 * 1024)
+            MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, smem, st, ql.atoms(), ql.start(),
+                      cl.atoms(), cl.start(), fg_dev, per_frame, tv.rp, sp, sink);
+    } else {
+        auto kern = cell_tile_kernel<MIC, SELF, Sink>;
+        if (smem > 24 * 1024)
+            MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, smem, st, ql.atoms(), ql.start(),
+                      cl.atoms(), cl.start(), fg_dev, per_frame, tv.chunks, sp, sink);
+    }
     MDA_CHECK_LAUNCH();
     return MDAGPU_OK;
 }
 
 template <class Sink>
 static int dispatch_hist(int mic, bool self, const CellList &ql, const CellList &cl,
-                         const FrameGeom *fg_dev, int per_frame, uint64_t nframes, uint64_t grid_x,
-                         int chunks, const SearchParams &sp, const Sink &sink, size_t smem,
-                         cudaStream_t st)
+                         const FrameGeom *fg_dev, int per_frame, uint64_t nframes, const Traversal &tv,
+                         const SearchParams &sp, const Sink &sink, size_t smem, cudaStream_t st)
 {
 #define HIST_CASE(M)                                                                               \
     case M:                                                                                        \
-        return self ? launch_hist<M, true>(ql, cl, fg_dev, per_frame, nframes, grid_x, chunks, sp, sink, smem, st) \
-                    : launch_hist<M, false>(ql, cl, fg_dev, per_frame, nframes, grid_x, chunks, sp, sink, smem, st)
+        return self ? launch_hist<M, true>(ql, cl, fg_dev, per_frame, nframes, tv, sp, sink, smem, st) \
+                    : launch_hist<M, false>(ql, cl, fg_dev, per_frame, nframes, tv, sp, sink, smem, st)
     switch (mic) {
         HIST_CASE(MIC_NONE);
         HIST_CASE(MIC_ORTHO_ROUND);
@@ -297,32 +284,52 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
     if (same) nb = na;
     if (nframes == 0 || na == 0 || nb == 0) return MDAGPU_OK;
 
-    // per-frame geometry on the host
+    // ---- per-frame geometry on the host ------------------------------------------------
+    // FastNS semantics (use_grid): the reference's own grid decides which pairs a
+    // triclinic search can see, so it is reproduced; for an orthorhombic cell every
+    // complete grid yields the same pair set and a finer one (cells >= cutoff/2, 5-cell
+    // window) is used when the box has room for it: fewer candidates per query.
     const uint64_t nbox = boxes_per_frame ? nframes : 1;
     std::vector<FrameGeom> fgs(nbox);
-    int64_t base = 0;
-    for (uint64_t f = 0; f < nbox; ++f) {
-        FrameGeom &fg = fgs[f];
-        const float *b6 = box6 ? box6 + 6 * f : nullptr;
-        const float *hh = h9 ? h9 + 9 * f : nullptr;
-        const bool tri = hh && (hh[3] != 0.0f || hh[6] != 0.0f || hh[7] != 0.0f);
-        if (use_grid) {
-            float mc = 0.0f;
-            grid_geometry_reference(cutoff, b6, hh, 1, &fg.grid, &mc);
-            // FastNS refuses such a cutoff (nsgrid.pyx:288-291)
-            MDA_REQUIRE(!(cutoff > (double)mc), "Cutoff %g too large for box (max %g)", cutoff, (double)mc);
-        } else {
-            grid_geometry_single(&fg.grid);
+    int W = 0;                                  // 0: cell_tile_kernel on the reference grid
+    const int tiled = !use_grid ? 0 : (mic == MIC_ORTHO_LAZY ? 2 : (mic == MIC_TRICLINIC ? 1 : 0));
+    for (int tryW = tiled; tryW >= 0 && W == 0; --tryW) {
+        int64_t base = 0;
+        bool ok = tryW > 0;
+        for (uint64_t f = 0; f < nbox; ++f) {
+            FrameGeom &fg = fgs[f];
+            const float *b6 = box6 ? box6 + 6 * f : nullptr;
+            const float *hh = h9 ? h9 + 9 * f : nullptr;
+            const bool tri = hh && (hh[3] != 0.0f || hh[6] != 0.0f || hh[7] != 0.0f);
+            if (mic == MIC_NONE && !b6) fg.box = make_box_params(BOX_NONE, nullptr);
+            else fg.box = tri ? make_box_params(BOX_TRICLINIC, hh) : make_box_params(BOX_ORTHO, b6);
+            if (use_grid) {
+                float mc = 0.0f;
+                grid_geometry_reference(cutoff, b6, hh, 1, &fg.grid, &mc);
+                // FastNS refuses such a cutoff (nsgrid.pyx:288-291)
+                MDA_REQUIRE(!(cutoff > (double)mc), "Cutoff %g too large for box (max %g)", cutoff, (double)mc);
+                if (tryW > 0 && mic == MIC_ORTHO_LAZY)
+                    grid_geometry_ortho_free(cutoff / tryW, b6, nullptr, 1, &fg.grid);
+            } else {
+                grid_geometry_single(&fg.grid);
+            }
+            if (tryW > 0) {
+                ok = ok && rowtile_supported(mic, fg.grid, fg.box, cutoff, tryW);
+                // very thin cells make the staged rows mostly bookkeeping
+                if (tryW > 1 && (double)nb / (double)fg.grid.ncell_total < 2.0) ok = false;
+            }
+            fg.cell_base = base;
+            base += fg.grid.ncell_total;
         }
-        if (mic == MIC_NONE && !b6) fg.box = make_box_params(BOX_NONE, nullptr);
-        else fg.box = tri ? make_box_params(BOX_TRICLINIC, hh) : make_box_params(BOX_ORTHO, b6);
-        fg.cell_base = base;
-        base += fg.grid.ncell_total;
+        if (ok) W = tryW;
     }
     const int64_t cells_per_frame = boxes_per_frame ? 0 : fgs[0].grid.ncell_total;
     double d_abs_err = 0.0;
-    if (mic == MIC_TRICLINIC)
-        for (uint64_t f = 0; f < nbox; ++f) d_abs_err = fmax(d_abs_err, tric_abs_err(fgs[f].box.h));
+    for (uint64_t f = 0; f < nbox; ++f) {
+        const double e = W ? rowtile_abs_err(mic, fgs[f].box, cutoff)
+                           : (mic == MIC_TRICLINIC ? tric_abs_err(fgs[f].box.h) : 0.0);
+        d_abs_err = fmax(d_abs_err, e);
+    }
 
     StagedIn a_in, b_in, thr_in;
     StagedOut cnt;
@@ -338,12 +345,16 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
     sp.use_filter = mic != MIC_ORTHO_ROUND;
     sp.stencil = use_grid ? 1 : 0;
 
-    const float lo = (float)r_lo;
+    // FP32 bin coordinate u = (d - lo) * inv_dr - 0.5: its error is the error of d (4e-7
+    // relative from the FP32 evaluation and the approximate sqrt, d_abs_err absolute)
+    // times inv_dr; pairs closer than twice that to a bin edge are decided in float64.
+    // A band >= 0.5 disables the FP32 path.
     const float inv_dr = (float)((double)nbins / (r_hi - r_lo));
-    // FP32 error of the bin coordinate u = (d - lo) * inv_dr: relative 1e-6 of d plus
-    // the absolute part; keep well clear of it (a band >= 0.5 disables the fast path)
-    const double u_err = (2e-6 * r_hi + 2.0 * d_abs_err) * (double)nbins / (r_hi - r_lo);
-    const float band = (float)fmax(2e-3, 10.0 * u_err);
+    const float c0 = (float)(-r_lo * (double)inv_dr - 0.5);
+    const double u_err = (4e-7 * fmax(fabs(r_hi), fabs(r_lo)) + d_abs_err) * (double)nbins / (r_hi - r_lo)
+                         + 2e-7 * (fabs((double)c0) + (double)nbins);
+    const float band = (float)fmax(5e-4, 2.0 * u_err);
+    const float band_lim = 0.5f - band;
     const float d2_fast_max = certain_threshold(d2_max, d_abs_err);
 
     // frames are processed in chunks that keep keys 32-bit and the grid within limits
@@ -389,31 +400,74 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
             if (rc) return rc;
         }
         const CellList &qq = same ? cl : ql;
-        const int nwords = (nbins + 1) / 2;
-        // threads per CTA ~ atoms per home cell (one query per thread)
-        const uint64_t max_cells = boxes_per_frame ? total_cells / fc + 1 : (uint64_t)cells_per_frame;
         const double occupancy = use_grid ? (double)na * (double)fc / (double)total_cells : (double)na;
-        int threads = occupancy > 128.0 ? 192 : (occupancy > 64.0 ? 128 : 64);
-        while (threads > 64 && (size_t)nwords * threads * 4 > 160 * 1024) threads = threads == 192 ? 128 : 64;
-        const bool fits = (size_t)nwords * threads * 4 <= 160 * 1024;
-        if (!fits) threads = 128;
-        int chunks = 1;
-        uint64_t grid_x = max_cells;
-        if (!use_grid) {                         // single cell: split the queries over CTAs
-            chunks = (int)((na + threads - 1) / threads);
-            grid_x = (uint64_t)chunks;
+
+        Traversal tv;
+        tv.row = W > 0;
+        tv.chunks = 1;
+        if (tv.row && mic == MIC_TRICLINIC) {
+            // an atom that the float64 cell arithmetic folded into a cell it does not lie
+            // in breaks the per-cell image prediction: take the per-pair kernel instead
+            unsigned bad[2] = { 0u, 0u };
+            MDA_CUDA(cudaMemcpyAsync(&bad[0], cl.inconsistent(), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            if (!same) MDA_CUDA(cudaMemcpyAsync(&bad[1], ql.inconsistent(), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            MDA_CUDA(cudaStreamSynchronize(st));
+            if (bad[0] | bad[1]) tv.row = 0;
+        }
+        int threads;
+        if (tv.row) {
+            threads = 128;
+            int nx_min = INT32_MAX, rows_max = 0;
+            for (uint64_t f = boxes_per_frame ? f0 : 0; f < (boxes_per_frame ? f0 + fc : 1); ++f) {
+                const GridGeom &g = fgs[f].grid;
+                nx_min = g.ncells[0] < nx_min ? g.ncells[0] : nx_min;
+                rows_max = g.ncells[1] * g.ncells[2] > rows_max ? g.ncells[1] * g.ncells[2] : rows_max;
+            }
+            int nx_max = 0;
+            for (uint64_t f = boxes_per_frame ? f0 : 0; f < (boxes_per_frame ? f0 + fc : 1); ++f)
+                nx_max = fgs[f].grid.ncells[0] > nx_max ? fgs[f].grid.ncells[0] : nx_max;
+            int R = (int)((double)threads / fmax(occupancy, 1e-9));
+            R = R < 1 ? 1 : (R > ROW_MAXR ? ROW_MAXR : R);
+            if (R > nx_max) R = nx_max;
+            const int runs = (nx_max + R - 1) / R;
+            R = (nx_max + runs - 1) / runs;              // even split of the row
+            tv.rp.W = W;
+            tv.rp.R = R;
+            tv.grid_x = (uint64_t)runs * (uint64_t)rows_max;
+            (void)nx_min;
+        } else {
+            // threads per CTA ~ atoms per home cell (one query per thread)
+            const uint64_t max_cells = boxes_per_frame ? total_cells / fc + 1 : (uint64_t)cells_per_frame;
+            threads = occupancy > 128.0 ? 192 : (occupancy > 64.0 ? 128 : 64);
+            tv.grid_x = max_cells;
+            if (boxes_per_frame) {
+                tv.grid_x = 0;
+                for (uint64_t f = f0; f < f0 + fc; ++f)
+                    tv.grid_x = (uint64_t)fgs[f].grid.ncell_total > tv.grid_x ? (uint64_t)fgs[f].grid.ncell_total : tv.grid_x;
+            }
+        }
+        // one 32-bit histogram per warp in shared memory
+        const size_t hist_bytes = (size_t)nbins * (threads / 32) * sizeof(uint32_t);
+        const bool fits = hist_bytes <= 160 * 1024;
+        if (!fits) threads = HistSinkGlobal::THREADS;
+        if (!tv.row && !use_grid) {                  // single cell: split the queries over CTAs
+            tv.chunks = (int)((na + threads - 1) / threads);
+            tv.grid_x = (uint64_t)tv.chunks;
         }
         SearchParams spc = sp;
         spc.include_self = same ? 1 : 0;
-#define RUN_HIST(SINK, SMEM)                                                                        \
+#define RUN_HIST(SINK)                                                                              \
     do {                                                                                           \
-        SINK sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, lo, inv_dr, band, d2_fast_max }; \
-        rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, grid_x, chunks, spc, sink, SMEM, st); \
+        SINK sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, c0, inv_dr, band_lim, d2_fast_max }; \
+        rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, hist_bytes, st); \
     } while (0)
-        if (!fits) RUN_HIST(HistSinkGlobal, 0);
-        else if (threads == 192) RUN_HIST(HistSink<192>, (size_t)nwords * 192 * 4);
-        else if (threads == 128) RUN_HIST(HistSink<128>, (size_t)nwords * 128 * 4);
-        else RUN_HIST(HistSink<64>, (size_t)nwords * 64 * 4);
+        if (!fits) {
+            HistSinkGlobal sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, (float)r_lo, inv_dr };
+            rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, 0, st);
+        }
+        else if (threads == 192) RUN_HIST(HistSink<192>);
+        else if (threads == 128) RUN_HIST(HistSink<128>);
+        else RUN_HIST(HistSink<64>);
 #undef RUN_HIST
         if (rc) return rc;
     }
