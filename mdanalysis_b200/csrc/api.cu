@@ -2,6 +2,8 @@
 // device selection, launch counter.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <map>
 #include <string>
 #include <vector>
@@ -27,6 +29,22 @@ void profile_begin(const char *name, cudaStream_t st)
 void profile_end(cudaStream_t st)
 {
     if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, st);
+}
+
+void pool_init()
+{
+    static bool done[64] = { false };
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    done[dev] = true;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) { cudaGetLastError(); return; }
+    size_t free_b = 0, total_b = 0;
+    unsigned long long keep = 0;
+    const char *env = getenv("MDAGPU_POOL_RETAIN_MB");
+    if (env && *env) keep = strtoull(env, nullptr, 10) << 20;
+    else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) keep = total_b / 4;
+    if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) cudaGetLastError();
 }
 
 char *err_buf()

@@ -45,6 +45,12 @@ static inline int num_sms()
 
 static inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
+// The library's scratch comes from the device's default stream-ordered pool.  By default
+// that pool hands everything back to the driver at the next synchronisation, which makes
+// every call pay for fresh mappings (tens of ms for the GiB-sized cell lists); keep up to
+// MDAGPU_POOL_RETAIN_MB (default: a quarter of the device memory) cached instead.
+void pool_init();
+
 // Stream-ordered scratch allocation that is released when the object dies.
 struct DevBuf {
     void *p = nullptr;
@@ -57,6 +63,7 @@ struct DevBuf {
     cudaError_t alloc(size_t n, cudaStream_t st)
     {
         release();
+        pool_init();
         s = st;
         bytes = n;
         if (n == 0) n = 16;
