@@ -50,7 +50,9 @@ void grid_geometry_ortho_free(double cutoff, const float *L3, const double *orig
 // ---------------------------------------------------------------------------
 // histogram sink
 // ---------------------------------------------------------------------------
-template <int T>
+// EXCL: an exclusion block is active (rdf.py:274-278), the weight of a pair then
+// depends on both atom indices.
+template <int T, bool EXCL>
 struct HistSink {
     static constexpr int THREADS = T;
     static constexpr bool FAST = true;
@@ -58,6 +60,7 @@ struct HistSink {
     unsigned long long *counts;   // [nbins] global histogram
     int nbins, excl_a, excl_b;
     float c0, inv_dr, band_lim, d2_fast_max;     // c0 = -lo*inv_dr - 0.5, band_lim = 0.5 - band
+    uint32_t hb;                  // shared address of this warp's histogram, biased (see begin())
 
     __device__ __forceinline__ uint32_t *mine() const
     {
@@ -68,38 +71,57 @@ struct HistSink {
     {
         extern __shared__ uint32_t s_hist[];
         for (int w = threadIdx.x; w < nbins * (T / 32); w += T) s_hist[w] = 0u;
+        // bin k of an accepted pair arrives as the bit pattern 0x4B400000 + k (see fast_bin)
+        hb = (uint32_t)__cvta_generic_to_shared(mine()) - 4u * 0x4B400000u;
     }
     __device__ __forceinline__ bool excluded(int i, int j) const
     {
-        return excl_a > 0 && (i / excl_a) == (j / excl_b);   // rdf.py:274-278
+        return EXCL && (i / excl_a) == (j / excl_b);   // rdf.py:274-278
     }
     // an unordered pair seen once stands for (i,j) and (j,i)
     template <bool SYM> __device__ __forceinline__ uint32_t weight_of(int i, int j) const
     {
+        if (!EXCL) return (SYM && i != j) ? 2u : 1u;
         if (!SYM) return excluded(i, j) ? 0u : 1u;
         if (i == j) return excluded(i, i) ? 0u : 1u;
         return (excluded(i, j) ? 0u : 1u) + (excluded(j, i) ? 0u : 1u);
     }
-    // FP32 binning: accepted only when the estimate is safely inside a bin and safely
-    // inside the cutoff; everything near a decision boundary goes to hit_w().
-    // floor(u) = round_to_nearest(u - 0.5) by the 2^23 trick; |u - 0.5 - k| < 0.5 - band
-    // <=> frac(u) in (band, 1 - band).  d2f == 0 sits on an edge and falls through.
-    template <bool SYM> __device__ __forceinline__ bool try_fast_w(int i, int j, float d2f)
+    // FP32 binning, straight-line: the pair is counted here only when the estimate is
+    // safely inside a bin and safely inside the cutoff (everything near a decision
+    // boundary is left to hit_w()).  floor(u) = round_to_nearest(u - 0.5) by the magic
+    // number trick: t = (u - 0.5) + 1.5 * 2^23 (unit spacing for |u| < 2^22, so also for the
+    // slightly negative values of d ~ 0) has the bin number in its low mantissa bits and
+    // fr = (u - 0.5) - k in [-0.5, 0.5];  |fr| < 0.5 - band  <=>  frac(u) in (band, 1 - band).
+    // The host guarantees 0 <= k < nbins for every d2f < d2_fast_max (else band_lim < 0).
+    // d2f == 0 sits on an edge, NaN compares false: both fall through.
+    // Split in two so that a caller can run the arithmetic of several candidates before
+    // any of their (order-preserving, volatile) shared-memory updates.
+    __device__ __forceinline__ bool fast_bin(float d2f, uint32_t &addr) const
     {
         float d;
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2f));
         const float u = fmaf(d, inv_dr, c0);
-        const float t = u + 8388608.0f;
-        const float fr = u - (t - 8388608.0f);
-        const int k = __float_as_int(t) - 0x4B000000;
-        if (!(d2f < d2_fast_max && fabsf(fr) < band_lim && (unsigned)k < (unsigned)nbins)) return false;
+        const float t = u + 12582912.0f;
+        const float fr = u - (t - 12582912.0f);
+        addr = hb + 4u * __float_as_uint(t);
+        return d2f < d2_fast_max && fabsf(fr) < band_lim;
+    }
+    template <bool SYM> __device__ __forceinline__ void fast_add(bool ok, uint32_t addr, int i, int j) const
+    {
+        if (!ok) return;
         uint32_t wgt = SYM ? 2u : 1u;
-        if (excl_a > 0) {
+        if (EXCL) {
             wgt = weight_of<SYM>(i, j);
-            if (!wgt) return true;
+            if (!wgt) return;
         }
-        atomicAdd(mine() + k, wgt);
-        return true;
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(wgt));
+    }
+    template <bool SYM> __device__ __forceinline__ bool try_fast_w(int i, int j, float d2f)
+    {
+        uint32_t addr;
+        const bool ok = fast_bin(d2f, addr);
+        fast_add<SYM>(ok, addr, i, j);
+        return ok;
     }
     __device__ __forceinline__ bool try_fast(int i, int j, float d2f) { return try_fast_w<false>(i, j, d2f); }
     template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t)
@@ -283,6 +305,9 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
     const bool same = (B == nullptr || B == A);
     if (same) nb = na;
     if (nframes == 0 || na == 0 || nb == 0) return MDAGPU_OK;
+    // a self RDF with exclusion_block=(1, 1) only drops the pairs (i, i)
+    int report_self = same ? 1 : 0;
+    if (same && excl_a == 1 && excl_b == 1) { excl_a = excl_b = 0; report_self = 0; }
 
     // ---- per-frame geometry on the host ------------------------------------------------
     // FastNS semantics (use_grid): the reference's own grid decides which pairs a
@@ -354,8 +379,13 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
     const double u_err = (4e-7 * fmax(fabs(r_hi), fabs(r_lo)) + d_abs_err) * (double)nbins / (r_hi - r_lo)
                          + 2e-7 * (fabs((double)c0) + (double)nbins);
     const float band = (float)fmax(5e-4, 2.0 * u_err);
-    const float band_lim = 0.5f - band;
-    const float d2_fast_max = certain_threshold(d2_max, d_abs_err);
+    // the straight-line FP32 path does not range-check the bin: it is enabled only when
+    // every pair it accepts (d2f < d2_fast_max) provably lands in [0, nbins)
+    double fast_d2 = d2_max;
+    if (r_hi > 0.0 && r_hi * r_hi < fast_d2) fast_d2 = r_hi * r_hi;
+    const bool fast_ok = r_lo <= 0.0 && r_hi > 0.0 && band < 0.25f;
+    const float band_lim = fast_ok ? 0.5f - band : -1.0f;
+    const float d2_fast_max = certain_threshold(fast_d2, d_abs_err);
 
     // frames are processed in chunks that keep keys 32-bit and the grid within limits
     uint64_t chunk = nframes;
@@ -455,20 +485,28 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
             tv.grid_x = (uint64_t)tv.chunks;
         }
         SearchParams spc = sp;
-        spc.include_self = same ? 1 : 0;
+        spc.include_self = report_self;
+#define COMMA ,
 #define RUN_HIST(SINK)                                                                              \
     do {                                                                                           \
-        SINK sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, c0, inv_dr, band_lim, d2_fast_max }; \
+        SINK sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, c0, inv_dr, band_lim, d2_fast_max, 0u }; \
         rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, hist_bytes, st); \
     } while (0)
         if (!fits) {
             HistSinkGlobal sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, (float)r_lo, inv_dr };
             rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, 0, st);
         }
-        else if (threads == 192) RUN_HIST(HistSink<192>);
-        else if (threads == 128) RUN_HIST(HistSink<128>);
-        else RUN_HIST(HistSink<64>);
+        else if (excl_a > 0) {
+            if (threads == 192) RUN_HIST(HistSink<192 COMMA true>);
+            else if (threads == 128) RUN_HIST(HistSink<128 COMMA true>);
+            else RUN_HIST(HistSink<64 COMMA true>);
+        } else {
+            if (threads == 192) RUN_HIST(HistSink<192 COMMA false>);
+            else if (threads == 128) RUN_HIST(HistSink<128 COMMA false>);
+            else RUN_HIST(HistSink<64 COMMA false>);
+        }
 #undef RUN_HIST
+#undef COMMA
         if (rc) return rc;
     }
     MDA_CUDA(cnt.finish());

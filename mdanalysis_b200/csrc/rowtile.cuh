@@ -11,32 +11,36 @@
 // Why this is exact although the inner loop is FP32:
 //  * Cells are sorted x-fastest, so the (up to 2W+1) cells a query must see in a
 //    neighbour row (dy, dz) are ONE contiguous run of the sorted atom array (three
-//    runs when the row wraps around the periodic x edge).  The run is staged in
-//    shared memory with the lattice translation of that (row, segment) already
-//    added: c' = c + a*h0 + b*h1 + c*h2, a,b,c in {-1,0,1}.  The translation is a
-//    property of the CELL pair, not of the atom pair: with >= 4 cells per periodic
-//    dimension (the reference's own rule, nsgrid.pyx:361-367) a wrapped stencil
-//    neighbour always needs exactly this image and a non-wrapped one never needs
-//    any (host-checked for triclinic cells, see rowtile_supported()).
-//  * The FP32 value |q - c'|^2 only FILTERS: it rejects pairs that are outside the
-//    cutoff by more than a rigorous error band, and bins pairs that are inside a
-//    histogram bin by more than that band.  Every pair inside a band is
-//    re-evaluated from the ORIGINAL float32 coordinates with the reference's
-//    float64 arithmetic (geom.cuh: pair_d2_exact / tric_image_d2), and that value
-//    alone takes the decision.  Pair lists always carry the exact float64 distance.
+//    runs when the row wraps around the periodic x edge).  The lattice translation
+//    of a (row, run) is a property of the CELL pair, not of the atom pair: with
+//    >= 2W+2 cells per periodic dimension a wrapped stencil neighbour always needs
+//    exactly this image and a non-wrapped one never needs any (host-checked for
+//    triclinic cells, see rowtile_supported()).  It is applied to the QUERY once per
+//    row / run:  q - (c + t) = (q - t) - c,  so the staged candidates are a verbatim
+//    copy of global memory.
+//  * The FP32 value |(q - t) - c|^2 only FILTERS: it rejects pairs that are outside
+//    the cutoff by more than a rigorous error band, and bins pairs that are inside a
+//    histogram bin by more than that band.  Every pair inside a band is re-evaluated
+//    from the ORIGINAL float32 coordinates with the reference's float64 arithmetic
+//    (geom.cuh: pair_d2_exact / tric_image_d2), and that value alone takes the
+//    decision.  Pair lists always carry the exact float64 distance.
 //
 // Work decomposition: blockIdx.x = (z * ny + y) * runs + run, blockIdx.y = frame.
-// A thread owns one query atom of the run (cell-sorted order, so a warp mostly
-// shares one home cell and all its lanes read the same staged candidate: LDS.128
-// broadcast); its window inside the staged row is [cell - W, cell + W].
+// A thread owns one query atom of the run (cell-sorted order); its window inside a
+// staged row is the cells [cell - W, cell + W].  Rows are streamed through a
+// two-buffer shared-memory ring by 1-D bulk copies (TMA, cp.async.bulk) that one
+// thread issues one row ahead; an mbarrier per buffer signals arrival, so the copy
+// of row r+1 runs under the arithmetic of row r and costs no issue slots.
 #pragma once
 #include "engine.cuh"
+#include "tma.cuh"
 
 namespace mdagpu {
 
-constexpr int ROW_TILE = 1024;       // staged candidates per piece (16 kB)
+constexpr int ROW_TILE = 512;        // staged candidates per buffer (8 kB, two buffers)
 constexpr int ROW_MAXR = 24;         // max home cells per CTA
-constexpr int ROW_MAXC = ROW_MAXR + 4 + 1;
+constexpr int ROW_MAXC = ROW_MAXR + 4;     // staged cells per row: R + 2W, W <= 2
+constexpr int ROW_MAXROWS = 25;      // (2W+1)^2
 
 struct RowParams {
     int W;              // window half-width in cells (1: cells >= cutoff, 2: cells >= cutoff/2)
@@ -96,6 +100,32 @@ static inline double rowtile_abs_err(int mic, const BoxParams &b, double cutoff)
     return s;
 }
 
+// One stencil row as staged in shared memory: up to three contiguous runs of the sorted
+// atom array (x-wrap on the left with image -h0, the in-range cells, x-wrap on the right
+// with image +h0), laid out back to back in "tile coordinates".
+struct RowInfo {
+    uint32_t g[3];      // first global slot of the left / main / right run
+    uint32_t end[3];    // tile coordinate where each run ends; end[2] = atoms in the row
+    int ib, ic;         // lattice image of the row (wrap along y, z)
+};
+
+// Exact re-evaluation of one pair from the original coordinates (rare: pairs inside an
+// error band of a decision boundary, or every accepted pair of a sink without an FP32
+// path).  (a, ib, ic) is the lattice image predicted for the cell pair.
+template <int MIC, bool SELF, class Sink>
+__device__ __noinline__ void row_exact(Sink sink, const BoxParams *box, double d2_max, double d2_min,
+                                       float4 q, float4 co, int a, int ib, int ic, uint64_t f)
+{
+    double d2;
+    if (MIC == MIC_TRICLINIC) {
+        D3 d = sep_f32(q.x, q.y, q.z, co.x, co.y, co.z), img;
+        d2 = tric_image_d2(d, box->h, a, -ib, -ic, img);
+    } else {
+        d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, co.x, co.y, co.z, *box);
+    }
+    if (d2 <= d2_max && d2 > d2_min) sink.template hit_w<SELF>(__float_as_int(q.w), __float_as_int(co.w), d2, f);
+}
+
 template <int MIC, bool SELF, class Sink>
 __global__ void __launch_bounds__(Sink::THREADS)
 row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
@@ -103,15 +133,24 @@ row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
                 const FrameGeom *__restrict__ fgs, int per_frame, RowParams rp, SearchParams sp, Sink sink)
 {
     constexpr int T = Sink::THREADS;
+    constexpr int NW = T / 32;
     __shared__ FrameGeom sfg;
-    __shared__ float4 tile[ROW_TILE];
-    __shared__ uint32_t s_off[ROW_MAXC + 1];      // tile offset of every staged cell (virtual x order)
-    __shared__ uint32_t s_qst[ROW_MAXR + 1];      // first query slot of every home cell of the run
+    __shared__ __align__(128) float4 tile[2][ROW_TILE];
+    __shared__ uint64_t bar[2];
+    __shared__ RowInfo s_row[ROW_MAXROWS];
+    __shared__ uint32_t s_off[ROW_MAXROWS][ROW_MAXC + 1];   // tile coordinate of every staged cell
+    __shared__ uint32_t s_qst[ROW_MAXR + 1];                // first query slot of every home cell
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t f = blockIdx.y;
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(fgs + (per_frame ? f : 0));
         uint32_t *dst = reinterpret_cast<uint32_t *>(&sfg);
-        for (int w = threadIdx.x; w < (int)(sizeof(FrameGeom) / 4); w += T) dst[w] = src[w];
+        for (int w = tid; w < (int)(sizeof(FrameGeom) / 4); w += T) dst[w] = src[w];
+    }
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     sink.begin();
     __syncthreads();
@@ -120,9 +159,81 @@ row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
     const int runs = (nx + R - 1) / R;
     if (blockIdx.x >= (unsigned)(runs * ny * nz)) return;          // frames may have fewer cells (uniform)
     const int xr = blockIdx.x % runs, y = (blockIdx.x / runs) % ny, z = blockIdx.x / (runs * ny);
-    const int x0 = xr * R, x1 = min(x0 + R, nx);
+    const int x0 = xr * R, x1 = min(x0 + R, nx), nh = x1 - x0;
     const int64_t base = per_frame ? sfg.cell_base : (int64_t)f * sfg.grid.ncell_total;
-    const BoxParams box = sfg.box;
+    const int px = sfg.grid.periodic[0], py = sfg.grid.periodic[1], pz = sfg.grid.periodic[2];
+    // rows of the stencil; SELF visits the half shell: the home row, then {dz = 0, dy > 0}, then {dz > 0}
+    const int side = 2 * W + 1;
+    const int nrows = SELF ? (W + 1) + W * side : side * side;
+    const int NC = nh + 2 * W;                                     // staged cells of a full row
+    auto row_dydz = [&](int r, int &dy, int &dz) {
+        if (SELF) {
+            if (r <= W) { dy = r; dz = 0; }
+            else { dz = 1 + (r - (W + 1)) / side; dy = (r - (W + 1)) % side - W; }
+        } else { dz = r / side - W; dy = r % side - W; }
+    };
+    // ---- phase 1: atoms per staged cell ------------------------------------------------
+    for (int idx = tid; idx < nrows * NC; idx += T) {
+        const int r = idx / NC, j = idx - r * NC;
+        int dy, dz;
+        row_dydz(r, dy, dz);
+        const bool home = SELF && r == 0;
+        int zz = z + dz, yy = y + dy;
+        bool ok = true;
+        if (zz < 0) { ok = ok && pz; zz += nz; } else if (zz >= nz) { ok = ok && pz; zz -= nz; }
+        if (yy < 0) { ok = ok && py; yy += ny; } else if (yy >= ny) { ok = ok && py; yy -= ny; }
+        int v = (home ? x0 : x0 - W) + j;
+        if (home && j >= nh + W) ok = false;
+        if (v < 0) { ok = ok && px; v += nx; } else if (v >= nx) { ok = ok && px; v -= nx; }
+        uint32_t cnt = 0;
+        if (ok) {
+            const int64_t cell = base + ((int64_t)zz * ny + yy) * nx + v;
+            cnt = c_start[cell + 1] - c_start[cell];
+        }
+        s_off[r][j] = cnt;
+    }
+    const int64_t home_row = base + ((int64_t)z * ny + y) * nx;
+    for (int j = tid; j <= nh; j += T) s_qst[j] = q_start[home_row + x0 + j];
+    __syncthreads();
+    // ---- phase 2: exclusive prefix per row, run descriptors ----------------------------------
+    for (int r = warp; r < nrows; r += NW) {
+        const bool home = SELF && r == 0;
+        const int ncell = home ? nh + W : NC;
+        const uint32_t cnt = lane < ncell ? s_off[r][lane] : 0u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        __syncwarp();
+        if (lane <= ncell) s_off[r][lane] = incl - cnt;              // lane == ncell: the row total
+        __syncwarp();
+        if (lane == 0) {
+            int dy, dz;
+            row_dydz(r, dy, dz);
+            int zz = z + dz, yy = y + dy, ib = 0, ic = 0;
+            if (zz < 0) { zz += nz; ic = -1; } else if (zz >= nz) { zz -= nz; ic = 1; }
+            if (yy < 0) { yy += ny; ib = -1; } else if (yy >= ny) { yy -= ny; ib = 1; }
+            const int vlo = home ? x0 : x0 - W, vhi = vlo + ncell - 1;
+            const int nleft = vlo < 0 ? -vlo : 0, nright = vhi >= nx ? vhi - nx + 1 : 0;
+            RowInfo ri;
+            ri.ib = ib; ri.ic = ic;
+            ri.end[0] = s_off[r][nleft];
+            ri.end[1] = s_off[r][ncell - nright];
+            ri.end[2] = s_off[r][ncell];
+            ri.g[0] = ri.g[1] = ri.g[2] = 0u;
+            if (ri.end[2]) {                                             // a populated row is inside the grid
+                const int64_t row = base + ((int64_t)zz * ny + yy) * nx;
+                if (ri.end[0]) ri.g[0] = c_start[row + nx - nleft];
+                if (ri.end[1] > ri.end[0]) ri.g[1] = c_start[row + (vlo < 0 ? 0 : vlo)];
+                if (ri.end[2] > ri.end[1]) ri.g[2] = c_start[row];
+            }
+            s_row[r] = ri;
+        }
+    }
+    __syncthreads();
+    const BoxParams &box = sfg.box;
     // lattice rows as FP32 vectors (orthorhombic: the box edges)
     float hx[3], hy[3], hz[3];
     if (MIC == MIC_TRICLINIC) {
@@ -134,122 +245,122 @@ row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
         hy[0] = 0.f; hy[1] = box.L[1]; hy[2] = 0.f;
         hz[0] = 0.f; hz[1] = 0.f; hz[2] = box.L[2];
     }
-    const int64_t home_row = base + ((int64_t)z * ny + y) * nx;
-    for (int j = threadIdx.x; j <= x1 - x0; j += T) s_qst[j] = q_start[home_row + x0 + j];
-    __syncthreads();
-    const uint32_t qs0 = s_qst[0], qs1 = s_qst[x1 - x0];
-
+    const uint32_t qs0 = s_qst[0], qs1 = s_qst[nh];
+    // stage (row r, tile offset p) -> buffer b: one thread issues up to three bulk copies
+    auto issue = [&](int r, uint32_t p, int b) {
+        const RowInfo &ri = s_row[r];
+        const uint32_t pe = min(p + (uint32_t)ROW_TILE, ri.end[2]);
+        mbar_expect_tx(&bar[b], (pe - p) * (uint32_t)sizeof(float4));
+        uint32_t sb = 0;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const uint32_t se = ri.end[s];
+            const uint32_t a = max(sb, p), e = min(se, pe);
+            if (a < e) bulk_g2s(&tile[b][a - p], c_atoms + ri.g[s] + (a - sb), (e - a) * (uint32_t)sizeof(float4), &bar[b]);
+            sb = se;
+        }
+    };
+    auto next_stage = [&](int &r, uint32_t &p) {
+        p += ROW_TILE;
+        if (p >= s_row[r].end[2]) {
+            p = 0;
+            do { ++r; } while (r < nrows && s_row[r].end[2] == 0u);
+        }
+    };
+    uint32_t si = 0;                                               // stages issued so far (buffer = si & 1)
     for (uint32_t qbase = qs0; qbase < qs1; qbase += T) {
-        const uint32_t qslot = qbase + threadIdx.x;
+        const uint32_t qslot = qbase + tid;
         const bool active = qslot < qs1;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        int cxl = 0;                                           // home cell of the query, relative to x0
+        int cxl = 0;                                               // home cell of the query, relative to x0
         if (active) {
             q = q_atoms[qslot];
-            while (cxl + 1 < x1 - x0 && s_qst[cxl + 1] <= qslot) ++cxl;
+            while (cxl + 1 < nh && s_qst[cxl + 1] <= qslot) ++cxl;
         }
         const int qi = __float_as_int(q.w);
-        if (SELF && sp.include_self && active) {               // capped_distance(x, x) reports (i, i)
+        if (SELF && sp.include_self && active) {                   // capped_distance(x, x) reports (i, i)
             const double d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, q.x, q.y, q.z, box);
             if (d2 <= sp.d2_max && d2 > sp.d2_min) sink.template hit_w<false>(qi, qi, d2, f);
         }
-        // rows of the stencil: SELF visits the half shell {dz > 0} U {dz = 0, dy > 0} U home row
-        for (int dz = SELF ? 0 : -W; dz <= W; ++dz) {
-            int zz = z + dz, ic = 0;
-            if (zz < 0) { if (!sfg.grid.periodic[2]) continue; zz += nz; ic = -1; }
-            else if (zz >= nz) { if (!sfg.grid.periodic[2]) continue; zz -= nz; ic = 1; }
-            for (int dy = (SELF && dz == 0) ? 0 : -W; dy <= W; ++dy) {
-                int yy = y + dy, ib = 0;
-                if (yy < 0) { if (!sfg.grid.periodic[1]) continue; yy += ny; ib = -1; }
-                else if (yy >= ny) { if (!sfg.grid.periodic[1]) continue; yy -= ny; ib = 1; }
-                const bool home = SELF && dz == 0 && dy == 0;
-                const int64_t row = base + ((int64_t)zz * ny + yy) * nx;
-                // virtual cells vlo .. vhi (inclusive) of this row are staged
-                const int vlo = home ? x0 : x0 - W, vhi = x1 - 1 + W;
-                const int ncell = vhi - vlo + 1;
-                __syncthreads();                               // previous row fully consumed
-                if (threadIdx.x < 32) {                        // warp 0: offsets of the staged cells
-                    uint32_t run = 0;
-                    for (int j0 = 0; j0 < ncell; j0 += 32) {
-                        const int j = j0 + (int)threadIdx.x;
-                        uint32_t cnt = 0;
-                        if (j < ncell) {
-                            int v = vlo + j;
-                            bool ok = true;
-                            if (v < 0) { ok = sfg.grid.periodic[0]; v += nx; }
-                            else if (v >= nx) { ok = sfg.grid.periodic[0]; v -= nx; }
-                            if (ok) cnt = c_start[row + v + 1] - c_start[row + v];
-                        }
-                        uint32_t incl = cnt;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-                            if ((int)threadIdx.x >= o) incl += u;
-                        }
-                        if (j < ncell) s_off[j] = run + incl - cnt;
-                        run += __shfl_sync(0xffffffffu, incl, 31);
-                    }
-                    if (threadIdx.x == 0) s_off[ncell] = run;
-                }
-                __syncthreads();
-                const uint32_t total = s_off[ncell];
-                // the three contiguous segments of the row: left wrap (image -h0), main, right wrap (+h0)
-                const int nleft = vlo < 0 ? -vlo : 0, nright = vhi >= nx ? vhi - nx + 1 : 0;
-                const uint32_t left_end = s_off[nleft], right_begin = s_off[ncell - nright];
-                const uint32_t g_left = (nleft && sfg.grid.periodic[0]) ? c_start[row + nx - nleft] : 0u;
-                const uint32_t g_main = c_start[row + (vlo < 0 ? 0 : vlo)];
-                const uint32_t g_right = c_start[row];
-                // translation of the row (b, c) and of the x segments (a)
-                const float ryx = (float)ib * hy[0] + (float)ic * hz[0];
-                const float ryy = (float)ib * hy[1] + (float)ic * hz[1];
-                const float ryz = (float)ib * hy[2] + (float)ic * hz[2];
-                // window of this thread in tile coordinates
-                uint32_t lo = 0, hi = 0;
-                if (active) {
-                    const int jl = home ? cxl : cxl;           // first staged cell of the window
-                    lo = s_off[jl];
-                    hi = s_off[min(jl + (home ? W : 2 * W) + 1, ncell)];
-                    if (home) lo = s_off[cxl] + (qslot - s_qst[cxl]) + 1;      // later atoms of the own cell
-                }
-                for (uint32_t p0 = 0; p0 < total; p0 += ROW_TILE) {
-                    const uint32_t pn = min((uint32_t)ROW_TILE, total - p0);
-                    if (p0) __syncthreads();
-                    for (uint32_t k = threadIdx.x; k < pn; k += T) {
-                        const uint32_t t = p0 + k;
-                        uint32_t slot;
-                        float sx = ryx, sy = ryy, sz = ryz;
-                        if (t < left_end) { slot = g_left + t; sx -= hx[0]; sy -= hx[1]; sz -= hx[2]; }
-                        else if (t < right_begin) slot = g_main + (t - left_end);
-                        else { slot = g_right + (t - right_begin); sx += hx[0]; sy += hx[1]; sz += hx[2]; }
-                        const float4 c = c_atoms[slot];
-                        tile[k] = make_float4(c.x + sx, c.y + sy, c.z + sz, c.w);
-                    }
-                    __syncthreads();
-                    if (!active) continue;
-                    const uint32_t a = max(lo, p0), b = min(hi, p0 + pn);
-#pragma unroll 4
-                    for (uint32_t t = a; t < b; ++t) {
-                        const float4 c = tile[t - p0];
-                        const float tx = q.x - c.x, ty = q.y - c.y, tz = q.z - c.z;
-                        const float d2f = fmaf(tx, tx, fmaf(ty, ty, tz * tz));
-                        if (d2f > sp.d2_filter) continue;
-                        if (Sink::FAST && sink.template try_fast_w<SELF>(qi, __float_as_int(c.w), d2f)) continue;
-                        // exact re-evaluation from the original coordinates
-                        const uint32_t slot = t < left_end ? g_left + t
-                                            : (t < right_begin ? g_main + (t - left_end) : g_right + (t - right_begin));
-                        const float4 co = c_atoms[slot];
-                        double d2;
-                        if (MIC == MIC_TRICLINIC) {
-                            const int ia = t < left_end ? -1 : (t >= right_begin ? 1 : 0);
-                            D3 d = sep_f32(q.x, q.y, q.z, co.x, co.y, co.z), img;
-                            d2 = tric_image_d2(d, box.h, -ia, -ib, -ic, img);
-                        } else {
-                            d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, co.x, co.y, co.z, box);
-                        }
-                        if (d2 <= sp.d2_max && d2 > sp.d2_min) sink.template hit_w<SELF>(qi, __float_as_int(co.w), d2, f);
-                    }
-                }
+        int r = 0;
+        uint32_t p = 0;
+        while (r < nrows && s_row[r].end[2] == 0u) ++r;
+        if (r < nrows && tid == 0) issue(r, p, (int)(si & 1u));
+        while (r < nrows) {
+            int rn = r;
+            uint32_t pn = p;
+            next_stage(rn, pn);
+            if (rn < nrows && tid == 0) issue(rn, pn, (int)((si + 1u) & 1u));
+            const RowInfo &ri = s_row[r];
+            const bool home = SELF && r == 0;
+            // window of this thread in tile coordinates
+            uint32_t lo = 0, hi = 0;
+            if (active) {
+                const int ncell = home ? nh + W : NC;
+                lo = s_off[r][cxl];
+                hi = s_off[r][min(cxl + (home ? W : 2 * W) + 1, ncell)];
+                if (home) lo += (qslot - s_qst[cxl]) + 1;          // later atoms of the own cell
             }
+            const uint32_t pe = min(p + (uint32_t)ROW_TILE, ri.end[2]);
+            lo = max(lo, p);
+            hi = min(hi, pe);
+            // the row's lattice translation goes onto the query: q - (c + t) = (q - t) - c
+            const float qrx = q.x - ((float)ri.ib * hy[0] + (float)ri.ic * hz[0]);
+            const float qry = q.y - ((float)ri.ib * hy[1] + (float)ri.ic * hz[1]);
+            const float qrz = q.z - ((float)ri.ib * hy[2] + (float)ri.ic * hz[2]);
+            mbar_wait(&bar[si & 1u], (si >> 1) & 1u);
+            const float4 *tb = tile[si & 1u];
+            uint32_t sb = 0;
+#pragma unroll 1
+            for (int s = 0; s < 3; ++s) {
+                const uint32_t se = ri.end[s];
+                const uint32_t a = max(lo, sb), e = min(hi, se);
+                const float sgn = (float)(1 - s);                  // left run: image -h0, i.e. q + h0
+                const float qx = qrx + sgn * hx[0], qy = qry + sgn * hx[1], qz = qrz + sgn * hx[2];
+                uint32_t t = a;
+                if constexpr (Sink::FAST) {
+                    // groups of four: straight-line FP32 filter + binning, one test for the rare exact path
+                    for (; t + 4 <= e; t += 4) {
+                        bool slow[4], ok[4];
+                        uint32_t addr[4];
+                        int cj[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 c = tb[t + k - p];
+                            const float tx = qx - c.x, ty = qy - c.y, tz = qz - c.z;
+                            const float d2f = fmaf(tx, tx, fmaf(ty, ty, tz * tz));
+                            ok[k] = sink.fast_bin(d2f, addr[k]);
+                            slow[k] = d2f <= sp.d2_filter && !ok[k];
+                            cj[k] = __float_as_int(c.w);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) sink.template fast_add<SELF>(ok[k], addr[k], qi, cj[k]);
+                        if (slow[0] | slow[1] | slow[2] | slow[3]) {
+#pragma unroll 1
+                            for (int k = 0; k < 4; ++k) {
+                                if (!((k == 0 && slow[0]) || (k == 1 && slow[1]) || (k == 2 && slow[2]) || (k == 3 && slow[3]))) continue;
+                                row_exact<MIC, SELF, Sink>(sink, &box, sp.d2_max, sp.d2_min, q, c_atoms[ri.g[s] + (t + k - sb)],
+                                                           1 - s, ri.ib, ri.ic, f);
+                            }
+                        }
+                    }
+                }
+                for (; t < e; ++t) {
+                    const float4 c = tb[t - p];
+                    const float tx = qx - c.x, ty = qy - c.y, tz = qz - c.z;
+                    const float d2f = fmaf(tx, tx, fmaf(ty, ty, tz * tz));
+                    bool done = false;
+                    if (Sink::FAST) done = sink.template try_fast_w<SELF>(qi, __float_as_int(c.w), d2f);
+                    if (d2f <= sp.d2_filter && !done)
+                        row_exact<MIC, SELF, Sink>(sink, &box, sp.d2_max, sp.d2_min, q, c_atoms[ri.g[s] + (t - sb)],
+                                                   1 - s, ri.ib, ri.ic, f);
+                }
+                sb = se;
+            }
+            __syncthreads();                                       // buffer si & 1 may be refilled
+            r = rn;
+            p = pn;
+            ++si;
         }
     }
     sink.end();

@@ -36,6 +36,15 @@ __global__ void __launch_bounds__(256) probe(double *out, float seed)
             if (OP == 8) atomicAdd(&hist[(threadIdx.x * 7 + it + k) & 255], 1u);   // ATOMS spread
             if (OP == 9) f[k] = (float)(int)f[k] + bf;                    // F2I + I2F + FADD
             if (OP == 10) d[k] = round(d[k]) + b;                         // double round (half away)
+            if (OP == 11 && (k & 1) == 0) {                               // FFMA2 (two FMAs per lane per instruction)
+                unsigned long long x, y = ((unsigned long long)__float_as_uint(af) << 32) | __float_as_uint(af),
+                                   z = ((unsigned long long)__float_as_uint(bf) << 32) | __float_as_uint(bf);
+                x = ((unsigned long long)__float_as_uint(f[k + 1]) << 32) | __float_as_uint(f[k]);
+                asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x) : "l"(x), "l"(y), "l"(z));
+                f[k] = __uint_as_float((unsigned)x); f[k + 1] = __uint_as_float((unsigned)(x >> 32));
+            }
+            if (OP == 12) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f[k])); f[k] = r; }   // MUFU.SQRT chain
+            if (OP == 13) { float2 t = reinterpret_cast<float2 *>(tile)[(it + k) & 511]; f[k] += t.x; }     // LDS.64 broadcast + FADD
         }
     }
     double s = 0;
@@ -85,5 +94,8 @@ int main()
     run<8>("ATOMS.ADD spread", out, sms, ghz, 1);
     run<9>("F2I + I2F + FADD", out, sms, ghz, 1);
     run<10>("round(double) + DADD", out, sms, ghz, 1);
+    run<11>("FFMA2 (2 FMA per lane-instr)", out, sms, ghz, 1);
+    run<12>("MUFU.SQRT", out, sms, ghz, 1);
+    run<13>("LDS.64 broadcast + FADD", out, sms, ghz, 1);
     return 0;
 }
