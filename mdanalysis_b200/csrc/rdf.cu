@@ -13,9 +13,11 @@
 // conversion-unit instruction: floor() is a magic-number add (the XU pipe runs at
 // 16 lanes/clk/SM on B200, profiles/microbench/pipes_b200.txt, and is kept for
 // the one MUFU.RSQ per step).
-#include "rowtile.cuh"
+#include "rowquad.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+#include <type_traits>
 #include <vector>
 
 namespace mdagpu {
@@ -212,6 +214,7 @@ struct CountSink {
 // How one chunk of frames is traversed.
 struct Traversal {
     int row;            // 1: row_tile_kernel (rowtile.cuh), 0: cell_tile_kernel (engine.cuh)
+    int quad;           // with row: row_quad_kernel (rowquad.cuh) when the sink and geometry allow it
     RowParams rp;
     uint64_t grid_x;
     int chunks;
@@ -223,6 +226,17 @@ static int launch_hist(const CellList &ql, const CellList &cl, const FrameGeom *
                        const Sink &sink, size_t smem, cudaStream_t st)
 {
     dim3 grid((unsigned)tv.grid_x, (unsigned)nframes);
+    if constexpr (MIC == MIC_ORTHO_LAZY && std::is_same<Sink, HistSink<128, false>>::value) {
+        if (tv.row && tv.quad) {
+            auto kern = row_quad_kernel<SELF, Sink>;
+            if (smem > 24 * 1024)
+                MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, smem, st, ql.atoms(), ql.start(),
+                          cl.atoms(), cl.start(), fg_dev, per_frame, tv.rp, sp, sink);
+            MDA_CHECK_LAUNCH();
+            return MDAGPU_OK;
+        }
+    }
     if (tv.row) {
         auto kern = row_tile_kernel<MIC, SELF, Sink>;
         if (smem > 24 * 1024)
@@ -349,10 +363,16 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
         if (ok) W = tryW;
     }
     const int64_t cells_per_frame = boxes_per_frame ? 0 : fgs[0].grid.ncell_total;
+    // the packed kernel (rowquad.cuh) folds the cutoff into the top histogram edge, has no
+    // exclusion blocks and keeps one 32-bit histogram per warp of a 128-thread CTA
+    const bool quad = W > 0 && mic == MIC_ORTHO_LAZY && r_hi > 0.0 && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max
+                      && excl_a == 0 && (size_t)nbins * 4 * sizeof(uint32_t) <= 160 * 1024
+                      && !getenv("MDAGPU_RDF_NO_QUAD");
     double d_abs_err = 0.0;
     for (uint64_t f = 0; f < nbox; ++f) {
-        const double e = W ? rowtile_abs_err(mic, fgs[f].box, cutoff)
-                           : (mic == MIC_TRICLINIC ? tric_abs_err(fgs[f].box.h) : 0.0);
+        const double e = quad ? rowquad_abs_err(fgs[f].box, cutoff)
+                         : W  ? rowtile_abs_err(mic, fgs[f].box, cutoff)
+                              : (mic == MIC_TRICLINIC ? tric_abs_err(fgs[f].box.h) : 0.0);
         d_abs_err = fmax(d_abs_err, e);
     }
 
@@ -434,6 +454,7 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
 
         Traversal tv;
         tv.row = W > 0;
+        tv.quad = quad;
         tv.chunks = 1;
         if (tv.row && mic == MIC_TRICLINIC) {
             // an atom that the float64 cell arithmetic folded into a cell it does not lie

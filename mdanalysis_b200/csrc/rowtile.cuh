@@ -126,46 +126,54 @@ __device__ __noinline__ void row_exact(Sink sink, const BoxParams *box, double d
     if (d2 <= d2_max && d2 > d2_min) sink.template hit_w<SELF>(__float_as_int(q.w), __float_as_int(co.w), d2, f);
 }
 
-template <int MIC, bool SELF, class Sink>
-__global__ void __launch_bounds__(Sink::THREADS)
-row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
-                const float4 *__restrict__ c_atoms, const uint32_t *__restrict__ c_start,
-                const FrameGeom *__restrict__ fgs, int per_frame, RowParams rp, SearchParams sp, Sink sink)
+// Bookkeeping of one CTA (shared memory): the frame geometry, the run descriptors of every
+// stencil row and the tile coordinate of every staged cell.
+struct RowBook {
+    FrameGeom fg;
+    RowInfo row[ROW_MAXROWS];
+    uint32_t off[ROW_MAXROWS][ROW_MAXC + 1];   // tile coordinate of every staged cell
+    uint32_t qst[ROW_MAXR + 1];                // first query slot of every home cell
+};
+
+// What row_prepare() derives for the CTA (identical in every thread).
+struct RowJob {
+    int nrows, nh, NC, W;
+    bool empty;                                // the CTA lies outside this frame's grid
+};
+
+// Phases shared by the row kernels: copy the frame geometry, count the atoms of every staged
+// cell, prefix them per row and describe the (up to three) runs of every row.
+// SELF visits the half shell: the home row, then {dz = 0, dy > 0}, then {dz > 0}.
+template <bool SELF, int T>
+__device__ __forceinline__ RowJob row_prepare(RowBook &bk, const uint32_t *__restrict__ q_start,
+                                              const uint32_t *__restrict__ c_start,
+                                              const FrameGeom *__restrict__ fgs, int per_frame,
+                                              RowParams rp, uint64_t f)
 {
-    constexpr int T = Sink::THREADS;
     constexpr int NW = T / 32;
-    __shared__ FrameGeom sfg;
-    __shared__ __align__(128) float4 tile[2][ROW_TILE];
-    __shared__ uint64_t bar[2];
-    __shared__ RowInfo s_row[ROW_MAXROWS];
-    __shared__ uint32_t s_off[ROW_MAXROWS][ROW_MAXC + 1];   // tile coordinate of every staged cell
-    __shared__ uint32_t s_qst[ROW_MAXR + 1];                // first query slot of every home cell
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t f = blockIdx.y;
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(fgs + (per_frame ? f : 0));
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&sfg);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&bk.fg);
         for (int w = tid; w < (int)(sizeof(FrameGeom) / 4); w += T) dst[w] = src[w];
     }
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    sink.begin();
     __syncthreads();
+    RowJob job;
     const int W = rp.W, R = rp.R;
-    const int nx = sfg.grid.ncells[0], ny = sfg.grid.ncells[1], nz = sfg.grid.ncells[2];
+    const int nx = bk.fg.grid.ncells[0], ny = bk.fg.grid.ncells[1], nz = bk.fg.grid.ncells[2];
     const int runs = (nx + R - 1) / R;
-    if (blockIdx.x >= (unsigned)(runs * ny * nz)) return;          // frames may have fewer cells (uniform)
+    job.W = W;
+    job.empty = blockIdx.x >= (unsigned)(runs * ny * nz);          // frames may have fewer cells (uniform)
+    job.nrows = job.nh = job.NC = 0;
+    if (job.empty) return job;
     const int xr = blockIdx.x % runs, y = (blockIdx.x / runs) % ny, z = blockIdx.x / (runs * ny);
     const int x0 = xr * R, x1 = min(x0 + R, nx), nh = x1 - x0;
-    const int64_t base = per_frame ? sfg.cell_base : (int64_t)f * sfg.grid.ncell_total;
-    const int px = sfg.grid.periodic[0], py = sfg.grid.periodic[1], pz = sfg.grid.periodic[2];
-    // rows of the stencil; SELF visits the half shell: the home row, then {dz = 0, dy > 0}, then {dz > 0}
+    const int64_t base = per_frame ? bk.fg.cell_base : (int64_t)f * bk.fg.grid.ncell_total;
+    const int px = bk.fg.grid.periodic[0], py = bk.fg.grid.periodic[1], pz = bk.fg.grid.periodic[2];
     const int side = 2 * W + 1;
     const int nrows = SELF ? (W + 1) + W * side : side * side;
     const int NC = nh + 2 * W;                                     // staged cells of a full row
+    job.nrows = nrows; job.nh = nh; job.NC = NC;
     auto row_dydz = [&](int r, int &dy, int &dz) {
         if (SELF) {
             if (r <= W) { dy = r; dz = 0; }
@@ -190,16 +198,16 @@ row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
             const int64_t cell = base + ((int64_t)zz * ny + yy) * nx + v;
             cnt = c_start[cell + 1] - c_start[cell];
         }
-        s_off[r][j] = cnt;
+        bk.off[r][j] = cnt;
     }
     const int64_t home_row = base + ((int64_t)z * ny + y) * nx;
-    for (int j = tid; j <= nh; j += T) s_qst[j] = q_start[home_row + x0 + j];
+    for (int j = tid; j <= nh; j += T) bk.qst[j] = q_start[home_row + x0 + j];
     __syncthreads();
     // ---- phase 2: exclusive prefix per row, run descriptors ----------------------------------
     for (int r = warp; r < nrows; r += NW) {
         const bool home = SELF && r == 0;
         const int ncell = home ? nh + W : NC;
-        const uint32_t cnt = lane < ncell ? s_off[r][lane] : 0u;
+        const uint32_t cnt = lane < ncell ? bk.off[r][lane] : 0u;
         uint32_t incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -207,7 +215,7 @@ row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
             if (lane >= o) incl += u;
         }
         __syncwarp();
-        if (lane <= ncell) s_off[r][lane] = incl - cnt;              // lane == ncell: the row total
+        if (lane <= ncell) bk.off[r][lane] = incl - cnt;              // lane == ncell: the row total
         __syncwarp();
         if (lane == 0) {
             int dy, dz;
@@ -219,9 +227,9 @@ row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
             const int nleft = vlo < 0 ? -vlo : 0, nright = vhi >= nx ? vhi - nx + 1 : 0;
             RowInfo ri;
             ri.ib = ib; ri.ic = ic;
-            ri.end[0] = s_off[r][nleft];
-            ri.end[1] = s_off[r][ncell - nright];
-            ri.end[2] = s_off[r][ncell];
+            ri.end[0] = bk.off[r][nleft];
+            ri.end[1] = bk.off[r][ncell - nright];
+            ri.end[2] = bk.off[r][ncell];
             ri.g[0] = ri.g[1] = ri.g[2] = 0u;
             if (ri.end[2]) {                                             // a populated row is inside the grid
                 const int64_t row = base + ((int64_t)zz * ny + yy) * nx;
@@ -229,10 +237,38 @@ row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
                 if (ri.end[1] > ri.end[0]) ri.g[1] = c_start[row + (vlo < 0 ? 0 : vlo)];
                 if (ri.end[2] > ri.end[1]) ri.g[2] = c_start[row];
             }
-            s_row[r] = ri;
+            bk.row[r] = ri;
         }
     }
     __syncthreads();
+    return job;
+}
+
+template <int MIC, bool SELF, class Sink>
+__global__ void __launch_bounds__(Sink::THREADS)
+row_tile_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
+                const float4 *__restrict__ c_atoms, const uint32_t *__restrict__ c_start,
+                const FrameGeom *__restrict__ fgs, int per_frame, RowParams rp, SearchParams sp, Sink sink)
+{
+    constexpr int T = Sink::THREADS;
+    __shared__ RowBook bk;
+    __shared__ __align__(128) float4 tile[2][ROW_TILE];
+    __shared__ uint64_t bar[2];
+    const int tid = threadIdx.x;
+    const uint64_t f = blockIdx.y;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    sink.begin();
+    const RowJob job = row_prepare<SELF, T>(bk, q_start, c_start, fgs, per_frame, rp, f);
+    if (job.empty) return;
+    const int W = job.W, nh = job.nh, NC = job.NC, nrows = job.nrows;
+    const FrameGeom &sfg = bk.fg;
+    RowInfo *s_row = bk.row;
+    uint32_t (*s_off)[ROW_MAXC + 1] = bk.off;
+    uint32_t *s_qst = bk.qst;
     const BoxParams &box = sfg.box;
     // lattice rows as FP32 vectors (orthorhombic: the box edges)
     float hx[3], hy[3], hz[3];
