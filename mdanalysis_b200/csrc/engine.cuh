@@ -51,9 +51,11 @@ __global__ void cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint6
                                 const FrameGeom *__restrict__ fg, int per_frame, int wrap,
                                 uint32_t *__restrict__ keys, uint32_t *__restrict__ counts,
                                 unsigned *__restrict__ flag);
-// exclusive scan of counts[0..n) into starts[0..n], starts[n] = total (single CTA, chunked)
+// exclusive scan of the per-cell counts into starts[], one CTA per frame (frame f starts at
+// f * n_atoms); starts[total_cells] = total
 __global__ void exclusive_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ starts,
-                                      uint64_t n);
+                                      const FrameGeom *__restrict__ fgs, int per_frame, uint64_t n_atoms,
+                                      uint64_t nframes);
 // sorted[starts[key] + slot] = {x,y,z,i}; cursor must be zeroed; wraps like cell_key_kernel
 __global__ void cell_scatter_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
                                     const FrameGeom *__restrict__ fg, int per_frame, int wrap,

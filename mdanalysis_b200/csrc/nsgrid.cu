@@ -111,14 +111,22 @@ cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
     }
 }
 
-// single CTA, 1024 threads, chunked with a running carry
+// One CTA per frame (1024 threads, chunked with a running carry): every frame holds
+// exactly n atoms, so the prefix of frame f starts at f * n and frames are independent.
 __global__ void __launch_bounds__(1024)
-exclusive_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ starts, uint64_t n)
+exclusive_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ starts,
+                      const FrameGeom *__restrict__ fgs, int per_frame, uint64_t n_atoms, uint64_t nframes)
 {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
+    const uint64_t f = blockIdx.x;
+    const FrameGeom &fg = fgs[per_frame ? f : 0];
+    const uint64_t n = (uint64_t)fg.grid.ncell_total;
+    const uint64_t cell0 = per_frame ? (uint64_t)fg.cell_base : f * n;
+    counts += cell0;
+    starts += cell0;
+    if (threadIdx.x == 0) carry = (uint32_t)(f * n_atoms);
     __syncthreads();
     for (uint64_t base = 0; base < n; base += 1024) {
         const uint64_t i = base + threadIdx.x;
@@ -149,7 +157,7 @@ exclusive_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict_
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) starts[n] = carry;
+    if (threadIdx.x == 0 && f + 1 == nframes) starts[n] = carry;
 }
 
 __global__ void __launch_bounds__(256)
@@ -202,8 +210,8 @@ int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameG
     MDA_LAUNCH(cell_key_kernel, grid, 256, 0, st, xyz, n, nframes, fg_dev, per_frame, wrap,
                cl->keys.as<uint32_t>(), cl->counts.as<uint32_t>(), cl->flag.as<unsigned>());
     MDA_CHECK_LAUNCH();
-    MDA_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, st, cl->counts.as<uint32_t>(),
-               cl->starts.as<uint32_t>(), total_cells);
+    MDA_LAUNCH(exclusive_scan_kernel, (unsigned)nframes, 1024, 0, st, cl->counts.as<uint32_t>(),
+               cl->starts.as<uint32_t>(), fg_dev, per_frame, n, nframes);
     MDA_CHECK_LAUNCH();
     MDA_LAUNCH(cell_scatter_kernel, grid, 256, 0, st, xyz, n, nframes, fg_dev, per_frame, wrap,
                cl->keys.as<uint32_t>(), cl->starts.as<uint32_t>(), cl->cursor.as<uint32_t>(),

@@ -299,6 +299,61 @@ bbox_kernel(const float *__restrict__ xyz, uint64_t total, float *__restrict__ l
     }
 }
 
+// Two-buffer upload ring for host-resident frames: piece k is copied on a private stream
+// into buffer k & 1 (after the kernels that read the buffer two pieces ago have finished)
+// and the compute stream waits for the copy before it touches the buffer.
+struct HostPipe {
+    const float *A = nullptr, *B = nullptr;
+    uint64_t na = 0, nb = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t ready[2] = { nullptr, nullptr }, freed[2] = { nullptr, nullptr };
+    DevBuf abuf[2], bbuf[2];
+    ~HostPipe()
+    {
+        for (int k = 0; k < 2; ++k) {
+            if (ready[k]) cudaEventDestroy(ready[k]);
+            if (freed[k]) cudaEventDestroy(freed[k]);
+        }
+        if (copy) {
+            cudaStreamSynchronize(copy);
+            cudaStreamDestroy(copy);
+        }
+    }
+    cudaError_t init(const float *a, const float *b, uint64_t na_, uint64_t nb_, uint64_t piece, cudaStream_t st)
+    {
+        A = a; B = b; na = na_; nb = nb_; compute = st;
+        cudaError_t e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking);
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+            e = cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = abuf[k].alloc(piece * na * 3 * sizeof(float), st);
+            if (e == cudaSuccess && B) e = bbuf[k].alloc(piece * nb * 3 * sizeof(float), st);
+            // the buffers become usable in stream order of `st`: the first copies wait for that
+            if (e == cudaSuccess) e = cudaEventRecord(freed[k], st);
+        }
+        return e;
+    }
+    cudaError_t upload(uint64_t piece_no, uint64_t f0, uint64_t fc)
+    {
+        const int k = (int)(piece_no & 1);
+        cudaError_t e = cudaStreamWaitEvent(copy, freed[k], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(abuf[k].p, A + f0 * na * 3, fc * na * 3 * sizeof(float), cudaMemcpyHostToDevice, copy);
+        if (e == cudaSuccess && B)
+            e = cudaMemcpyAsync(bbuf[k].p, B + f0 * nb * 3, fc * nb * 3 * sizeof(float), cudaMemcpyHostToDevice, copy);
+        if (e == cudaSuccess) e = cudaEventRecord(ready[k], copy);
+        return e;
+    }
+    cudaError_t acquire(uint64_t piece_no, const float **a, const float **b)
+    {
+        const int k = (int)(piece_no & 1);
+        *a = abuf[k].as<float>();
+        *b = B ? bbuf[k].as<float>() : nullptr;
+        return cudaStreamWaitEvent(compute, ready[k], 0);
+    }
+    cudaError_t release(uint64_t piece_no) { return cudaEventRecord(freed[(int)(piece_no & 1)], compute); }
+};
+
 }  // namespace mdagpu
 
 using namespace mdagpu;
@@ -376,10 +431,8 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
         d_abs_err = fmax(d_abs_err, e);
     }
 
-    StagedIn a_in, b_in, thr_in;
+    StagedIn thr_in;
     StagedOut cnt;
-    MDA_CUDA(a_in.init(A, nframes * na * 3 * sizeof(float), space, st));
-    if (!same) MDA_CUDA(b_in.init(B, nframes * nb * 3 * sizeof(float), space, st));
     MDA_CUDA(thr_in.init(thresholds, (size_t)(nbins + 1) * sizeof(double), MDAGPU_HOST, st));   // always a host array
     MDA_CUDA(cnt.init(counts, (size_t)nbins * sizeof(unsigned long long), space, st, true));
 
@@ -419,9 +472,30 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
         if (chunk > by_cells) chunk = by_cells;
     }
 
+    // Host input is streamed: frames go up in pieces on a second stream into a two-buffer
+    // ring while the previous piece is being binned (the reference-facing call hands over
+    // HOST arrays; 400 MB per 1000 frames of C2 would otherwise sit in front of the kernels).
+    HostPipe pipe;
+    if (space == MDAGPU_HOST) {
+        uint64_t piece = (nframes + 7) / 8;
+        if (piece < 16) piece = 16;
+        if (chunk > piece) chunk = piece;
+        MDA_CUDA(pipe.init(A, same ? nullptr : B, na, nb, chunk, st));
+    }
+
     DevBuf fg_dev;
-    for (uint64_t f0 = 0; f0 < nframes; f0 += chunk) {
+    uint64_t piece_no = 0;
+    for (uint64_t f0 = 0; f0 < nframes; f0 += chunk, ++piece_no) {
         const uint64_t fc = (nframes - f0 < chunk) ? nframes - f0 : chunk;
+        const float *a_dev = A + f0 * na * 3, *b_dev = same ? nullptr : B + f0 * nb * 3;
+        if (space == MDAGPU_HOST) {
+            if (piece_no == 0) MDA_CUDA(pipe.upload(0, f0, fc));
+            if (f0 + chunk < nframes) {
+                const uint64_t f1 = f0 + chunk, fn = (nframes - f1 < chunk) ? nframes - f1 : chunk;
+                MDA_CUDA(pipe.upload(piece_no + 1, f1, fn));
+            }
+            MDA_CUDA(pipe.acquire(piece_no, &a_dev, &b_dev));
+        }
         uint64_t total_cells;
         if (boxes_per_frame) {
             // re-base this chunk's cells at zero
@@ -441,11 +515,10 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
         }
         const FrameGeom *fgd = fg_dev.as<FrameGeom>();
         CellList cl, ql;
-        int rc = build_cell_list((same ? a_in.as<float>() : b_in.as<float>()) + f0 * nb * 3, nb, fc, fgd,
-                                 boxes_per_frame, total_cells, wrap, st, &cl);
+        int rc = build_cell_list(same ? a_dev : b_dev, nb, fc, fgd, boxes_per_frame, total_cells, wrap, st, &cl);
         if (rc) return rc;
         if (!same) {
-            rc = build_cell_list(a_in.as<float>() + f0 * na * 3, na, fc, fgd, boxes_per_frame,
+            rc = build_cell_list(a_dev, na, fc, fgd, boxes_per_frame,
                                  total_cells, wrap, st, &ql);
             if (rc) return rc;
         }
@@ -529,6 +602,7 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
 #undef RUN_HIST
 #undef COMMA
         if (rc) return rc;
+        if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
     }
     MDA_CUDA(cnt.finish());
     if (space == MDAGPU_HOST) MDA_CUDA(cudaStreamSynchronize(st));

@@ -34,8 +34,8 @@
 
 namespace mdagpu {
 
-constexpr int WQ_CAP = 2560;              // padded candidates the tile holds (30 kB: 13 rows of a liquid)
-constexpr int WQ_SLOW = 96;               // queued exact evaluations per warp
+constexpr int WQ_CAP = 1280;              // padded candidates the tile holds (30 kB: 13 rows of a liquid)
+constexpr int WQ_SLOW = 48;               // queued exact evaluations per warp
 constexpr float QUAD_FAR = 1.0e18f;       // sentinel coordinate: (2e18)^2 * 3 is finite in FP32
 
 __device__ __forceinline__ uint32_t ru4(uint32_t v) { return (v + 3u) & ~3u; }
@@ -198,7 +198,7 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
 }
 
 template <bool SELF, class Sink>
-__global__ void __launch_bounds__(Sink::THREADS)
+__global__ void __launch_bounds__(Sink::THREADS, 7)
 row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
                 const float4 *__restrict__ c_atoms, const uint32_t *__restrict__ c_start,
                 const FrameGeom *__restrict__ fgs, int per_frame, RowParams rp, SearchParams sp, Sink sink)
