@@ -103,6 +103,19 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def ncu_traffic(n_frames, n_atoms):
+    """DRAM bytes per launch of the pair-histogram kernel from the committed ncu capture
+    (profiles/r01e_traffic.json), scaled to this run's frames x atoms; None without it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as fh:
+            t = json.load(fh)
+        per_atom = (t["dram_bytes_read"] + t["dram_bytes_write"]) / (t["frames_per_launch"] * t["atoms"])
+        return {"dram_bytes_per_launch": per_atom * n_frames * n_atoms, "unit": "B",
+                "algorithmic_bytes_per_launch": 16.0 * n_frames * n_atoms, "source": t["source"]}
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def make_frames(n_frames, n_atoms, rank):
     rng = np.random.default_rng(SEED + 1000 * rank)
     return (rng.random((n_frames, n_atoms, 3), dtype=np.float32) * np.float32(BOX_L))
@@ -329,7 +342,7 @@ def run_ours(args, rank, world, local_rank):
     k_launches, k_ms = prof.get(kname, (0, 0.0))
     achieved = (ALGO_FLOP_PER_FRAME * (N / N_O) ** 2 * F * k_launches / (k_ms / 1e3) / 1e12) if k_ms > 0 else 0.0
     roofline = {"bound": "fp32", "kernel": kname, "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": achieved / FP32_PEAK_TFLOPS, "traffic": None,
+                "frac": achieved / FP32_PEAK_TFLOPS, "traffic": ncu_traffic(F, N),
                 "peak_kind": "nominal non-tensor FP32 at 1965 MHz (MEASURED_PEAKS.json has no FP32 figure)",
                 "kernel_ms_per_launch": (k_ms / k_launches) if k_launches else None,
                 "kernel_share_of_step": (k_ms / ms) if ms > 0 else None,

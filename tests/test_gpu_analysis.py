@@ -263,8 +263,8 @@ def test_qcp_trajectory_streamed_kernel(oracle, n, F, weighted):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["ortho_w2", "ortho_w2_ab_excl", "ortho_w1", "ortho_perframe",
-                                  "tric_w1", "tric_w1_ab", "tric_perframe", "tric_flat"])
+@pytest.mark.parametrize("case", ["ortho_w2", "ortho_w2_ab", "ortho_w2_ab_excl", "ortho_w1", "ortho_w1_ab",
+                                  "ortho_perframe", "tric_w1", "tric_w1_ab", "tric_perframe", "tric_flat"])
 def test_interrdf_row_traversal(oracle, case):
     """The row-staged traversal (csrc/rowtile.cuh): every grid flavour it takes, against
     the oracle's FastNS + np.histogram, bit-exact counts."""
@@ -275,7 +275,7 @@ def test_interrdf_row_traversal(oracle, case):
     F = 3
     kw = {}
     if case.startswith("ortho"):
-        if case == "ortho_w1":
+        if case.startswith("ortho_w1"):
             N, rmax, nb = 4000, 9.0, 90
             dims = np.tile(np.array([40, 37, 52, 90, 90, 90], dtype=np.float32), (F, 1))
         else:
@@ -312,3 +312,49 @@ def test_interrdf_row_traversal(oracle, case):
     g1d = g1.to_device()
     got_d = InterRDF(g1d, g1d if g2 is g1 else g2.to_device(), nbins=nb, range=(0.0, rmax), **kw).run()
     assert np.array_equal(got_d.results.count, want["count"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["dense_groups", "dense_long_rows", "lattice_on_edges", "small_cutoff_range"])
+def test_interrdf_quad_kernel_against_row_kernel(oracle, case, monkeypatch):
+    """The packed kernel (csrc/rowquad.cuh) against the per-pair row kernel it replaces
+    (itself pinned to the oracle above) on inputs the oracle is too slow for: stencil rows
+    that need several staging groups, rows longer than the tile, atoms sitting exactly on
+    histogram edges (every pair goes through the float64 queue), and a cutoff that is not
+    the top edge (the packed kernel must decline)."""
+    from mdanalysis_b200.analysis.rdf import InterRDF
+    from mdanalysis_b200 import FrameBlock
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    kw = dict(nbins=60, range=(0.0, 3.0))
+    if case == "dense_groups":
+        N, box = 60000, np.array([30, 31, 29, 90, 90, 90], dtype=np.float32)
+        kw = dict(nbins=80, range=(0.0, 4.0))
+        pos = (rng.random((2, N, 3)) * box[:3] * 1.1).astype(np.float32)
+    elif case == "dense_long_rows":
+        N, box = 800000, np.array([20, 22, 24, 90, 90, 90], dtype=np.float32)
+        pos = (rng.random((1, N, 3)) * box[:3]).astype(np.float32)
+    elif case == "lattice_on_edges":
+        # simple cubic lattice with spacing = 2 bin widths: most distances are multiples of edges
+        n1, a = 24, 0.5
+        g = np.arange(n1, dtype=np.float32) * a
+        pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(1, -1, 3).astype(np.float32)
+        box = np.array([n1 * a] * 3 + [90, 90, 90], dtype=np.float32)
+        kw = dict(nbins=16, range=(0.0, 2.0))
+    else:
+        N, box = 9000, np.array([47, 52, 61, 90, 90, 90], dtype=np.float32)
+        pos = (rng.random((2, N, 3)) * box[:3]).astype(np.float32)
+        kw = dict(nbins=140, range=(0.5, 7.0))
+    blk = FrameBlock(pos, box).to_device()
+    got = InterRDF(blk, None, **kw).run().results.count
+    monkeypatch.setenv("MDAGPU_RDF_NO_QUAD", "1")
+    want = InterRDF(blk, None, **kw).run().results.count
+    monkeypatch.delenv("MDAGPU_RDF_NO_QUAD")
+    assert np.array_equal(got, want)
+    assert got.sum() > 0
+    if case == "lattice_on_edges":
+        ref = oracle.interrdf(pos, pos, box, nbins=kw["nbins"], rrange=kw["range"])
+        assert np.array_equal(got, ref["count"])
+    # host-resident frames go through the upload ring in pieces
+    got_h = InterRDF(FrameBlock(pos, box), None, **kw).run().results.count
+    assert np.array_equal(got_h, want)
