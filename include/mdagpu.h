@@ -112,6 +112,23 @@ MDAGPU_API int mdagpu_coord_transform(float *coords, uint64_t n, const double *m
 MDAGPU_API int mdagpu_wrap(float *coords, uint64_t n, int box_mode, const float *box, int space,
                 mdagpu_stream_t stream);
 
+/* minimize_vectors  lib/distances.py:1790-1830 -> _minimize_vectors_{ortho,triclinic}
+ * (c_distances.pyx:372-414).  vectors/out: [n,3] float32 (is_double = 0) or float64; box: 3
+ * (BOX_ORTHO) or 9 (BOX_TRICLINIC, flattened triclinic_vectors) values of the SAME dtype,
+ * host memory.  Same dtype out as in, as the reference. */
+MDAGPU_API int mdagpu_minimize_vectors(const void *vectors, uint64_t n, int is_double, int box_mode,
+                            const void *box, void *out, int space, mdagpu_stream_t stream);
+
+/* Contacts._single_frame  analysis/contacts.py:486-499: r = distance_array(A, B, box)[mask].
+ * Evaluates only the listed elements (idx_i into A, idx_j into B) of every frame's distance
+ * matrix: out[f, p] = |B[f, idx_j[p]] - A[f, idx_i[p]]| with distance_array's arithmetic.
+ * A [nframes, na, 3], B [nframes, nb, 3] float32; boxes: 3 (ortho) or 9 (triclinic) float32
+ * per frame (boxes_per_frame) or once, host memory; out float64 [nframes, npairs]. */
+MDAGPU_API int mdagpu_pair_list_distances(const float *A, uint64_t na, const float *B, uint64_t nb,
+                               uint64_t nframes, const long long *idx_i, const long long *idx_j,
+                               uint64_t npairs, int box_mode, const float *boxes, int boxes_per_frame,
+                               double *out, int space, mdagpu_stream_t stream);
+
 /* ---- FastNS: cell-list neighbour search (lib/nsgrid.pyx) ----------------------- */
 typedef struct mdagpu_grid mdagpu_grid;
 typedef struct mdagpu_pairs mdagpu_pairs;
@@ -216,6 +233,16 @@ MDAGPU_API int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
                           int use_grid, const double *thresholds, int nbins, double r_lo,
                           double r_hi, int excl_a, int excl_b, unsigned long long *counts,
                           int space, mdagpu_stream_t stream);
+
+/* InterRDF_s  analysis/rdf.py:585-597: as mdagpu_rdf_accumulate, but one histogram per
+ * (site i of A, site j of B): counts is uint64 [na, nb, nbins] (nb = na when B is NULL /
+ * the same array), accumulated into. */
+MDAGPU_API int mdagpu_rdf_sites_accumulate(const float *A, uint64_t na, const float *B, uint64_t nb,
+                                uint64_t nframes, const float *box6, const float *h9,
+                                int boxes_per_frame, int mic, int wrap, double cutoff,
+                                double d2_max, int use_grid, const double *thresholds,
+                                int nbins, double r_lo, double r_hi,
+                                unsigned long long *counts, int space, mdagpu_stream_t stream);
 
 /* Fused self_distance_array -> contact count / per-atom degree
  * (analysis/contacts.py:315-338 `d <= radius`, analysis/distances.py:102-108)

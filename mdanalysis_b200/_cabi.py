@@ -39,6 +39,8 @@ SIGNATURES = {
     "mdagpu_calc_dihedrals": (_i, [_vp, _vp, _vp, _vp, _u64, _i, _vp, _vp, _i, _vp]),
     "mdagpu_coord_transform": (_i, [_vp, _u64, _vp, _i, _vp]),
     "mdagpu_wrap": (_i, [_vp, _u64, _i, _vp, _i, _vp]),
+    "mdagpu_minimize_vectors": (_i, [_vp, _u64, _i, _i, _vp, _vp, _i, _vp]),
+    "mdagpu_pair_list_distances": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _u64, _i, _vp, _i, _vp, _i, _vp]),
     "mdagpu_grid_create": (_i, [_d, _vp, _u64, _vp, _vp, _i, _i, _vp, C.POINTER(_vp)]),
     "mdagpu_grid_info": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(C.c_float)]),
     "mdagpu_grid_geometry": (_i, [_d, _vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(C.c_float)]),
@@ -53,6 +55,8 @@ SIGNATURES = {
     "mdagpu_qcp_trajectory": (_i, [_vp, _u64, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mdagpu_rdf_accumulate": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,
                                    _d, _d, _i, _i, _vp, _i, _vp]),
+    "mdagpu_rdf_sites_accumulate": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,
+                                         _d, _d, _vp, _i, _vp]),
     "mdagpu_contacts_self": (_i, [_vp, _u64, _u64, _i, _vp, _d, _d, _vp, _vp, _i, _vp]),
 }
 

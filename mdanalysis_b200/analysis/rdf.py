@@ -214,3 +214,106 @@ class InterRDF(BlockAnalysis):
             box_vol = self.volume_cum / self.n_frames
             norm = norm * (N / box_vol)
         self.results.rdf = self.results.count / norm
+
+
+class InterRDF_s(BlockAnalysis):
+    """Site-specific radial distribution functions (``analysis/rdf.py:351-678``).
+
+    u      FrameBlock | [F, n, 3] array / CUDA tensor holding every atom (with unit cells)
+    ags    list of ``[sites1, sites2]`` pairs of index arrays into ``u``
+    Results as the reference: ``results.count[k]`` / ``results.rdf[k]`` have shape
+    ``(len(sites1), len(sites2), nbins)``, ``results.indices[k] = [sites1, sites2]``,
+    ``get_cdf()`` the cumulative counts.  All frames of a pair of groups are binned by one
+    call (``mdagpu_rdf_sites_accumulate``: per-site histograms in device memory).
+    """
+
+    def __init__(self, u, ags, nbins=75, range=(0.0, 15.0), norm="rdf", density=False, dimensions=None,
+                 **kwargs):
+        blk = as_block(u, dimensions)
+        super().__init__(blk, **kwargs)
+        self.ags = [[np.asarray(a, dtype=np.int64), np.asarray(b, dtype=np.int64)] for a, b in ags]
+        self.norm = str(norm).lower()
+        self.rdf_settings = {"bins": nbins, "range": range}
+        if self.norm not in ["rdf", "density", "none"]:
+            raise ValueError(f"'{self.norm}' is an invalid norm. Use 'rdf', 'density' or 'none'.")
+        if density:
+            self.norm = "density"
+
+    def _prepare(self, blk):
+        count, edges = np.histogram([-1], **self.rdf_settings)
+        self.results.count = [np.zeros((len(a), len(b), len(count)), dtype=np.float64) for a, b in self.ags]
+        self.results.edges = edges
+        self.results.bins = 0.5 * (edges[:-1] + edges[1:])
+        self.volume_cum = 0
+        self._maxrange = self.rdf_settings["range"][1]
+
+    _frame_modes = InterRDF._frame_modes
+
+    def _compute(self, blk):
+        nbins = len(self.results.edges) - 1
+        lo, hi = float(self.results.edges[0]), float(self.results.edges[-1])
+        thr = histogram_thresholds(self.results.edges)
+        rc2 = float(self._maxrange) * float(self._maxrange)
+        d2_brute = float(sqrt_le_threshold(self._maxrange))
+        dev = blk.on_device
+        for k, (ia, ib) in enumerate(self.ags):
+            A_all, B_all = blk.select(ia).positions, blk.select(ib).positions
+            na, nb = len(ia), len(ib)
+            if na == 0 or nb == 0:
+                continue
+            modes = self._frame_modes(blk, na, nb)
+            if dev:
+                import torch
+                counts = torch.zeros((na, nb, nbins), dtype=torch.int64, device=A_all.device)
+            else:
+                counts = np.zeros((na, nb, nbins), dtype=np.uint64)
+            for mode in sorted(set(modes)):
+                use_grid, mic, wrap = mode
+                fidx = np.flatnonzero([m == mode for m in modes])
+                whole = len(fidx) == blk.n_frames
+                sel = fidx if not dev else None
+                if dev and not whole:
+                    import torch
+                    sel = torch.as_tensor(fidx, device=A_all.device)
+                A = A_all if whole else A_all[sel]
+                B = B_all if whole else B_all[sel]
+                dims = blk.dimensions if whole else blk.dimensions[fidx]
+                const = bool((dims == dims[0]).all())
+                box6 = np.ascontiguousarray(dims[:1] if const else dims, dtype=np.float32)
+                h9 = np.ascontiguousarray([triclinic_vectors(b).reshape(9) for b in box6], dtype=np.float32)
+                d2_max = rc2 if use_grid else d2_brute
+                if dev:
+                    A, B = A.contiguous(), B.contiguous()
+                    rc = load().mdagpu_rdf_sites_accumulate(
+                        tensor_ptr(A), na, tensor_ptr(B), nb, len(fidx), ptr(box6), ptr(h9), int(not const), mic,
+                        wrap, float(self._maxrange), d2_max, use_grid, ptr(thr), nbins, lo, hi,
+                        tensor_ptr(counts), DEVICE, current_stream(A))
+                else:
+                    A, B = np.ascontiguousarray(A), np.ascontiguousarray(B)
+                    rc = load().mdagpu_rdf_sites_accumulate(
+                        ptr(A), na, ptr(B), nb, len(fidx), ptr(box6), ptr(h9), int(not const), mic, wrap,
+                        float(self._maxrange), d2_max, use_grid, ptr(thr), nbins, lo, hi, ptr(counts), HOST, None)
+                check(rc)
+            host_counts = counts.cpu().numpy() if dev else counts
+            self.results.count[k] += host_counts.astype(np.float64)
+        if self.norm == "rdf":
+            for box in blk.dimensions:                   # rdf.py:599-600
+                self.volume_cum += box_volume(box)
+
+    def _conclude(self):
+        norm = self.n_frames
+        if self.norm in ["rdf", "density"]:
+            vols = np.power(self.results.edges, 3)
+            norm = norm * (4 / 3 * np.pi * np.diff(vols))
+        if self.norm == "rdf":
+            norm = norm * (1 / (self.volume_cum / self.n_frames))
+        self.results.indices = []
+        self.results.rdf = []
+        for k, (ia, ib) in enumerate(self.ags):
+            self.results.indices.append([ia, ib])
+            self.results.rdf.append(self.results.count[k] / norm)
+
+    def get_cdf(self):
+        """Cumulative counts per site pair, averaged over frames (rdf.py:619-640)."""
+        self.results.cdf = [np.cumsum(c, axis=2) / self.n_frames for c in self.results.count]
+        return self.results.cdf

@@ -182,6 +182,34 @@ struct HistSinkGlobal {
     __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t f) { hit_w<false>(i, j, d2, f); }
 };
 
+// InterRDF_s (rdf.py:585-597): one histogram per (site of A, site of B) pair,
+// counts[(i * nb + j) * nbins + k]; an unordered pair of a self search stands for (i, j)
+// and (j, i).
+struct HistSinkSites {
+    static constexpr int THREADS = 128;
+    static constexpr bool FAST = false;
+    const double *thr;
+    unsigned long long *counts;
+    int nbins;
+    uint64_t nb;
+    float lo, inv_dr;
+    __device__ __forceinline__ bool try_fast(int, int, float) { return false; }
+    template <bool SYM> __device__ __forceinline__ bool try_fast_w(int, int, float) { return false; }
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ void end() {}
+    template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t)
+    {
+        if (!(d2 >= thr[0]) || !(d2 <= thr[nbins])) return;
+        int k = (int)((sqrtf((float)d2) - lo) * inv_dr);
+        k = k < 0 ? 0 : (k > nbins - 1 ? nbins - 1 : k);
+        while (k > 0 && d2 < thr[k]) --k;
+        while (k < nbins - 1 && d2 >= thr[k + 1]) ++k;
+        atomicAdd(&counts[((uint64_t)i * nb + (uint64_t)j) * (uint64_t)nbins + k], 1ull);
+        if (SYM && i != j) atomicAdd(&counts[((uint64_t)j * nb + (uint64_t)i) * (uint64_t)nbins + k], 1ull);
+    }
+    __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t f) { hit_w<false>(i, j, d2, f); }
+};
+
 // contacts: pair count per frame and optional per-atom degree
 struct CountSink {
     static constexpr int THREADS = 128;
@@ -358,12 +386,12 @@ struct HostPipe {
 
 using namespace mdagpu;
 
-extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B, uint64_t nb,
-                                     uint64_t nframes, const float *box6, const float *h9,
-                                     int boxes_per_frame, int mic, int wrap, double cutoff,
-                                     double d2_max, int use_grid, const double *thresholds,
-                                     int nbins, double r_lo, double r_hi, int excl_a, int excl_b,
-                                     unsigned long long *counts, int space, mdagpu_stream_t stream)
+static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint64_t nb,
+                               uint64_t nframes, const float *box6, const float *h9,
+                               int boxes_per_frame, int mic, int wrap, double cutoff,
+                               double d2_max, int use_grid, const double *thresholds,
+                               int nbins, double r_lo, double r_hi, int excl_a, int excl_b,
+                               unsigned long long *counts, int per_site, int space, mdagpu_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     MDA_REQUIRE(A && thresholds && counts, "mdagpu_rdf_accumulate: NULL argument");
@@ -420,7 +448,7 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
     const int64_t cells_per_frame = boxes_per_frame ? 0 : fgs[0].grid.ncell_total;
     // the packed kernel (rowquad.cuh) folds the cutoff into the top histogram edge, has no
     // exclusion blocks and keeps one 32-bit histogram per warp of a 128-thread CTA
-    const bool quad = W > 0 && mic == MIC_ORTHO_LAZY && r_hi > 0.0 && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max
+    const bool quad = !per_site && W > 0 && mic == MIC_ORTHO_LAZY && r_hi > 0.0 && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max
                       && excl_a == 0 && (size_t)nbins * 4 * sizeof(uint32_t) <= 160 * 1024
                       && !getenv("MDAGPU_RDF_NO_QUAD");
     double d_abs_err = 0.0;
@@ -434,7 +462,8 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
     StagedIn thr_in;
     StagedOut cnt;
     MDA_CUDA(thr_in.init(thresholds, (size_t)(nbins + 1) * sizeof(double), MDAGPU_HOST, st));   // always a host array
-    MDA_CUDA(cnt.init(counts, (size_t)nbins * sizeof(unsigned long long), space, st, true));
+    const size_t n_hist = per_site ? (size_t)na * (size_t)nb : 1;          // histograms in `counts`
+    MDA_CUDA(cnt.init(counts, n_hist * (size_t)nbins * sizeof(unsigned long long), space, st, true));
 
     SearchParams sp;
     sp.d2_max = d2_max;
@@ -572,7 +601,7 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
         }
         // one 32-bit histogram per warp in shared memory
         const size_t hist_bytes = (size_t)nbins * (threads / 32) * sizeof(uint32_t);
-        const bool fits = hist_bytes <= 160 * 1024;
+        const bool fits = !per_site && hist_bytes <= 160 * 1024;
         if (!fits) threads = HistSinkGlobal::THREADS;
         if (!tv.row && !use_grid) {                  // single cell: split the queries over CTAs
             tv.chunks = (int)((na + threads - 1) / threads);
@@ -586,7 +615,11 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
         SINK sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, c0, inv_dr, band_lim, d2_fast_max, 0u }; \
         rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, hist_bytes, st); \
     } while (0)
-        if (!fits) {
+        if (per_site) {
+            HistSinkSites sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, nb, (float)r_lo, inv_dr };
+            rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, 0, st);
+        }
+        else if (!fits) {
             HistSinkGlobal sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, (float)r_lo, inv_dr };
             rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, 0, st);
         }
@@ -607,6 +640,30 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
     MDA_CUDA(cnt.finish());
     if (space == MDAGPU_HOST) MDA_CUDA(cudaStreamSynchronize(st));
     return MDAGPU_OK;
+}
+
+extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B, uint64_t nb,
+                                     uint64_t nframes, const float *box6, const float *h9,
+                                     int boxes_per_frame, int mic, int wrap, double cutoff,
+                                     double d2_max, int use_grid, const double *thresholds,
+                                     int nbins, double r_lo, double r_hi, int excl_a, int excl_b,
+                                     unsigned long long *counts, int space, mdagpu_stream_t stream)
+{
+    return rdf_accumulate_impl(A, na, B, nb, nframes, box6, h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
+                               use_grid, thresholds, nbins, r_lo, r_hi, excl_a, excl_b, counts, 0, space, stream);
+}
+
+extern "C" int mdagpu_rdf_sites_accumulate(const float *A, uint64_t na, const float *B, uint64_t nb,
+                                           uint64_t nframes, const float *box6, const float *h9,
+                                           int boxes_per_frame, int mic, int wrap, double cutoff,
+                                           double d2_max, int use_grid, const double *thresholds,
+                                           int nbins, double r_lo, double r_hi,
+                                           unsigned long long *counts, int space, mdagpu_stream_t stream)
+{
+    MDA_REQUIRE(na * nb <= (1ull << 26), "mdagpu_rdf_sites_accumulate: %llu x %llu site pairs is too many "
+                "(one histogram each)", (unsigned long long)na, (unsigned long long)(B && B != A ? nb : na));
+    return rdf_accumulate_impl(A, na, B, nb, nframes, box6, h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
+                               use_grid, thresholds, nbins, r_lo, r_hi, 0, 0, counts, 1, space, stream);
 }
 
 extern "C" int mdagpu_contacts_self(const float *xyz, uint64_t n, uint64_t nframes, int box_mode,

@@ -511,3 +511,38 @@ def apply_PBC(coords, box, backend="cuda"):
     else:
         _run("triclinic_pbc", args=(work, b), backend=backend)
     return work[0] if single else work
+
+
+def minimize_vectors(vectors, box):
+    """Apply the minimum image convention to an array of vectors (lib/distances.py:1790-1830).
+
+    ``vectors`` is ``(n, 3)`` float32 or float64 (NumPy array or torch CUDA tensor); the
+    result has the same dtype, as in the reference (``check_coords(enforce_copy=False,
+    enforce_dtype=False)``).  The box is converted to the vectors' dtype first (:1822).
+    """
+    boxtype, b = check_box(box)
+    if is_tensor(vectors):
+        import torch
+        if vectors.ndim != 2 or vectors.shape[1] != 3:
+            raise ValueError(f"minimize_vectors(): vectors.shape must be (n, 3) got {tuple(vectors.shape)}")
+        if vectors.dtype not in (torch.float32, torch.float64):
+            raise TypeError("minimize_vectors(): vectors must be float32 or float64")
+        v = vectors.contiguous()
+        out = torch.empty_like(v)
+        bb = np.ascontiguousarray(b.astype(np.float64 if v.dtype == torch.float64 else np.float32).ravel())
+        check(load().mdagpu_minimize_vectors(tensor_ptr(v), v.shape[0], int(v.dtype == torch.float64),
+                                             BOX_ORTHO if boxtype == "ortho" else BOX_TRICLINIC, ptr(bb),
+                                             tensor_ptr(out), DEVICE, current_stream(v)))
+        return out
+    (v,), _ = prepare_coords("minimize_vectors", [("vectors", vectors)], enforce_copy=False, enforce_dtype=False,
+                             allow_single=False)
+    if v.dtype not in (np.float32, np.float64):
+        # the reference's fused-type kernels accept nothing else (c_distances.pyx:372, 394)
+        raise TypeError(f"minimize_vectors(): no kernel for dtype {v.dtype}")
+    vc = np.ascontiguousarray(v)
+    out = np.empty_like(vc)
+    bb = np.ascontiguousarray(b.astype(vc.dtype).ravel())
+    check(load().mdagpu_minimize_vectors(ptr(vc), vc.shape[0], int(vc.dtype == np.float64),
+                                         BOX_ORTHO if boxtype == "ortho" else BOX_TRICLINIC, ptr(bb),
+                                         ptr(out), HOST, None))
+    return out

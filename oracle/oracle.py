@@ -230,6 +230,62 @@ def calc_dihedrals(a, b, c, d, box=None, impl="port", openmp=False):
     return _tuple_fn("dihedrals", (a, b, c, d), box, impl, openmp)
 
 
+def _c_round(x):
+    """libm round(): half away from zero, on float64 (c_distances.pyx:38 `cround`)."""
+    x = np.asarray(x, dtype=np.float64)
+    t = np.trunc(x)
+    return t + np.where(np.abs(x - t) >= 0.5, np.sign(x), 0.0)
+
+
+def minimize_vectors(vectors, box):
+    """lib/distances.py:1790-1830 -> c_distances.pyx:272-414, restated with NumPy in the
+    dtype the generated C evaluates each operation in (fused type = the vectors' dtype)."""
+    boxtype, b = check_box(box)
+    v = np.array(vectors)
+    T = v.dtype.type
+    if T not in (np.float32, np.float64):
+        raise TypeError("minimize_vectors: float32 or float64 only")
+    b = np.asarray(b).astype(T)
+    out = v.copy()
+    if boxtype == BOX_ORTHO:
+        inv = (T(1.0) / b).astype(T)
+        for k in range(3):
+            if b[k] > 0:
+                s = (inv[k] * out[:, k]).astype(T)
+                s64 = s.astype(np.float64)
+                out[:, k] = (np.float64(b[k]) * (s64 - _c_round(s64))).astype(T)
+        return out
+    b = b.ravel()
+    inv = [T(1.0) / b[0], T(1.0) / b[4], T(1.0) / b[8]]
+    dx = [out[:, 0].copy(), out[:, 1].copy(), out[:, 2].copy()]
+    s = _c_round((inv[2] * dx[2]).astype(T)).astype(T)
+    dx[0] = (dx[0] - (s * b[6]).astype(T)).astype(T)
+    dx[1] = (dx[1] - (s * b[7]).astype(T)).astype(T)
+    dx[2] = (dx[2] - (s * b[8]).astype(T)).astype(T)
+    s = _c_round((inv[1] * dx[1]).astype(T)).astype(T)
+    dx[0] = (dx[0] - (s * b[3]).astype(T)).astype(T)
+    dx[1] = (dx[1] - (s * b[4]).astype(T)).astype(T)
+    s = _c_round((inv[0] * dx[0]).astype(T)).astype(T)
+    dx[0] = (dx[0] - (s * b[0]).astype(T)).astype(T)
+    n = len(v)
+    best = np.full(n, np.finfo(T).max, dtype=T)
+    m = np.zeros((n, 3), dtype=T)
+    for ix in (-1, 0, 1):
+        rx = (dx[0] + T(b[0] * T(ix))).astype(T)
+        for iy in (-1, 0, 1):
+            ry0 = (rx + T(b[3] * T(iy))).astype(T)
+            ry1 = (dx[1] + T(b[4] * T(iy))).astype(T)
+            for iz in (-1, 0, 1):
+                rz0 = (ry0 + T(b[6] * T(iz))).astype(T)
+                rz1 = (ry1 + T(b[7] * T(iz))).astype(T)
+                rz2 = (dx[2] + T(b[8] * T(iz))).astype(T)
+                dsq = (((rz0 * rz0).astype(T) + (rz1 * rz1).astype(T)).astype(T) + (rz2 * rz2).astype(T)).astype(T)
+                better = dsq < best
+                best = np.where(better, dsq, best)
+                m[better, 0], m[better, 1], m[better, 2] = rz0[better], rz1[better], rz2[better]
+    return m
+
+
 def coord_transform(coords, matrix, impl="port"):
     """include/calc_distances.h:533-555 (in place on a copy)."""
     xyz = _f32(coords).copy()
@@ -640,3 +696,75 @@ def interrdf(pos_a, pos_b, dimensions, nbins=75, rrange=(0.0, 15.0), norm="rdf",
     res["rdf"] = count / normv
     res["volume_cum"] = volume_cum
     return res
+
+
+# --------------------------------------------------------------------------
+# InterRDF_s (analysis/rdf.py:573-640)
+# --------------------------------------------------------------------------
+def interrdf_s(pos, ags, dimensions, nbins=75, rrange=(0.0, 15.0), norm="rdf"):
+    """pos [F, n, 3] float32, ags = [[idx1, idx2], ...]; returns count / rdf / cdf lists."""
+    pos = np.asarray(pos, dtype=np.float32)
+    F = len(pos)
+    dims = np.asarray(dimensions, dtype=np.float32)
+    if dims.ndim == 1:
+        dims = np.broadcast_to(dims, (F, 6))
+    c0, edges = np.histogram([-1], bins=nbins, range=rrange)
+    counts = [np.zeros((len(a), len(b), len(c0)), dtype=np.float64) for a, b in ags]
+    volume_cum = 0.0
+    for f in range(F):
+        for i, (a, b) in enumerate(ags):
+            pairs, dist = capped_distance(np.ascontiguousarray(pos[f][a]), np.ascontiguousarray(pos[f][b]),
+                                          rrange[1], box=dims[f])
+            for j, (i1, i2) in enumerate(pairs):          # rdf.py:593-595
+                c, _ = np.histogram(dist[j], bins=nbins, range=rrange)
+                counts[i][i1, i2, :] += c
+        if norm == "rdf":
+            volume_cum += box_volume(dims[f])
+    normv = float(F)
+    if norm in ("rdf", "density"):
+        normv = normv * (4 / 3 * np.pi * np.diff(np.power(edges, 3)))
+    if norm == "rdf":
+        normv = normv * (1 / (volume_cum / F))
+    return {"count": counts, "edges": edges, "rdf": [c / normv for c in counts],
+            "cdf": [np.cumsum(c, axis=2) / F for c in counts]}
+
+
+# --------------------------------------------------------------------------
+# Contacts (analysis/contacts.py:231-338, 341-499)
+# --------------------------------------------------------------------------
+def contacts_timeseries(pos, idx_a, idx_b, refs, dimensions=None, method="hard_cut", radius=4.5,
+                        pbc=True, ref_box=None, kwargs=None):
+    """pos [F, n, 3]; refs = [(refA [na,3], refB [nb,3]), ...]; returns timeseries [F, len(refs)+1]."""
+    kwargs = kwargs or {}
+    pos = np.asarray(pos, dtype=np.float32)
+    F = len(pos)
+    dims = None
+    if dimensions is not None and pbc:
+        dims = np.asarray(dimensions, dtype=np.float32)
+        if dims.ndim == 1:
+            dims = np.broadcast_to(dims, (F, 6))
+    r0s, masks = [], []
+    for refA, refB in refs:
+        r0 = distance_array(np.asarray(refA, dtype=np.float32), np.asarray(refB, dtype=np.float32),
+                            box=ref_box if pbc else None)
+        r0s.append(r0)
+        masks.append(r0 <= radius)
+    ts = np.empty((F, len(refs) + 1))
+    for f in range(F):
+        ts[f, 0] = f
+        d = distance_array(np.ascontiguousarray(pos[f][idx_a]), np.ascontiguousarray(pos[f][idx_b]),
+                           box=None if dims is None else dims[f])
+        for i, (mask, r0) in enumerate(zip(masks, r0s), 1):
+            r, rr0 = d[mask], r0[mask]
+            with np.errstate(invalid="ignore", divide="ignore"):
+                if method == "hard_cut":
+                    q = (r <= rr0).sum() / r.size
+                elif method == "radius_cut":
+                    q = (r <= radius).sum() / r.size
+                elif method == "soft_cut":
+                    beta, lam = kwargs.get("beta", 5.0), kwargs.get("lambda_constant", 1.8)
+                    q = (1 / (1 + np.exp(beta * (r - lam * rr0)))).sum() / len(rr0)
+                else:
+                    q = method(r, rr0, **kwargs)
+            ts[f, i] = q
+    return ts
