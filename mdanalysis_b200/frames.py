@@ -94,7 +94,9 @@ class FrameBlock:
         traj = u.trajectory
         sl = slice(start, stop, step)
         frames = np.arange(len(traj))[sl]
-        pos = traj.timeseries(atomgroup, start=start, stop=stop, step=step, order="fac")
+        # one bulk read of every frame (MemoryReader.timeseries has inclusive-stop semantics and
+        # rejects stop=None, coordinates/memory.py:545-567), sliced here
+        pos = np.asarray(traj.timeseries(atomgroup, order="fac"))[sl]
         dims, times = [], []
         for ts in traj[sl]:
             dims.append(None if ts.dimensions is None else np.array(ts.dimensions, dtype=np.float32))

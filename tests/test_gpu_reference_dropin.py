@@ -1,0 +1,156 @@
+"""-m gpu: the CUDA backend plugged into the REAL, unmodified reference.
+
+baseline/_ref holds MDAnalysis 2.8.0-dev0 built out of tree from /root/reference (git-ignored,
+shipped to the GPU box by gpurun; recipe in DESIGN.md).  When it is there, these tests call the
+reference's own front ends with ``backend='cuda'`` (mdanalysis_b200.register.install) next to
+``backend='serial'``, and run the reference's analysis classes on a MemoryReader universe next
+to the GPU classes fed from the same universe.  Skipped when baseline/_ref is absent.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+
+@pytest.fixture(scope="module")
+def mda():
+    if not os.path.isdir(os.path.join(REF, "MDAnalysis")):
+        pytest.skip("baseline/_ref (the built reference) is not present")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    warnings.filterwarnings("ignore")
+    import MDAnalysis
+    import mdanalysis_b200.register as reg
+    reg.install(patch_capped=True)
+    return MDAnalysis
+
+
+BOXES = {
+    "none": None,
+    "ortho": np.array([30, 25, 40, 90, 90, 90], dtype=np.float32),
+    "tric": np.array([40, 35, 50, 70, 80, 100], dtype=np.float32),
+}
+
+
+@pytest.mark.parametrize("bname", list(BOXES))
+def test_lib_distances_backend_cuda(mda, bname):
+    import MDAnalysis.lib.distances as D
+    assert "cuda" in D._distances
+    rng = np.random.default_rng(5)
+    box = BOXES[bname]
+    a, b, c, d = [((rng.random((n, 3)) * 5 - 2) * 35).astype(np.float32) for n in (301, 257, 301, 301)]
+    for args, fn in (((a, b), D.distance_array), ((a,), D.self_distance_array), ((a, c), D.calc_bonds)):
+        assert np.array_equal(fn(*args, box=box, backend="cuda"), fn(*args, box=box, backend="serial"))
+    for args, fn in (((a, c, d), D.calc_angles), ((a, c, d, a[::-1].copy()), D.calc_dihedrals)):
+        got, want = fn(*args, box=box, backend="cuda"), fn(*args, box=box, backend="serial")
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-12, equal_nan=True)      # atan2: <= 1e-5 relative
+    if box is not None:
+        for fn in (D.apply_PBC, D.transform_RtoS, D.transform_StoR):
+            assert np.array_equal(fn(a, box, backend="cuda"), fn(a, box, backend="serial"))
+    # results written into a caller-owned (here: non-contiguous) array, as _check_result_array allows
+    res = np.zeros((301, 514), dtype=np.float64)[:, ::2]
+    D.distance_array(a, b, box=box, result=res, backend="cuda")
+    assert np.array_equal(res, D.distance_array(a, b, box=box, backend="serial"))
+    with pytest.raises(ValueError):
+        D.distance_array(a, b, box=box, backend="nope")
+
+
+@pytest.mark.parametrize("bname", list(BOXES))
+@pytest.mark.parametrize("method", ["bruteforce", "nsgrid", "pkdtree"])
+def test_capped_distance_backend_cuda(mda, bname, method):
+    import MDAnalysis.lib.distances as D
+    rng = np.random.default_rng(9)
+    box = BOXES[bname]
+    a, b = (rng.random((400, 3)) * 30).astype(np.float32), (rng.random((300, 3)) * 30).astype(np.float32)
+
+    def canon(p, d, self_pairs=False):
+        p = np.asarray(p).reshape(-1, 2)
+        if self_pairs:
+            p = np.sort(p, axis=1)
+        o = np.lexsort((p[:, 1], p[:, 0]))
+        return p[o], np.asarray(d)[o]
+    for mn in (None, 1.5):
+        pw, dw = canon(*D.capped_distance(a, b, 5.0, min_cutoff=mn, box=box, method=method))
+        pg, dg = canon(*D.capped_distance(a, b, 5.0, min_cutoff=mn, box=box, method=method, backend="cuda"))
+        assert np.array_equal(pg, pw) and np.allclose(dg, dw, rtol=1e-12)
+        pw, dw = canon(*D.self_capped_distance(a, 5.0, min_cutoff=mn, box=box, method=method), True)
+        pg, dg = canon(*D.self_capped_distance(a, 5.0, min_cutoff=mn, box=box, method=method, backend="cuda"), True)
+        assert np.array_equal(pg, pw) and np.allclose(dg, dw, rtol=1e-12)
+
+
+def _universe(mda, xyz, dims, masses=None):
+    u = mda.Universe.empty(xyz.shape[1], trajectory=True)
+    if masses is not None:
+        u.add_TopologyAttr("masses", masses)
+    u.load_new(xyz.copy(), order="fac", **({} if dims is None else {"dimensions": dims}))
+    return u
+
+
+def test_interrdf_class_against_reference(mda):
+    from MDAnalysis.analysis.rdf import InterRDF as RefRDF, InterRDF_s as RefRDFs
+    from mdanalysis_b200 import FrameBlock
+    from mdanalysis_b200.analysis.rdf import InterRDF, InterRDF_s
+    rng = np.random.default_rng(21)
+    F, N = 3, 2500
+    box = np.array([32, 34, 30, 90, 90, 90], dtype=np.float32)
+    pos = (rng.random((F, N, 3)) * box[:3] * 1.1).astype(np.float32)
+    u = _universe(mda, pos, np.tile(box, (F, 1)))
+    for kw in ({}, {"exclusion_block": (1, 1)}, {"norm": "density"}):
+        want = RefRDF(u.atoms, u.atoms, nbins=90, range=(0.0, 9.0), **kw).run()
+        blk = FrameBlock.from_atomgroup(u.atoms)                # bulk ingest: timeseries(order='fac')
+        got = InterRDF(blk, blk, nbins=90, range=(0.0, 9.0), **kw).run()
+        assert np.array_equal(got.results.count, want.results.count)
+        assert np.array_equal(got.results.edges, want.results.edges)
+        assert np.allclose(got.results.rdf, want.results.rdf, rtol=1e-12)
+    sites = [[np.array([0, 1]), np.arange(50, 400)]]
+    want = RefRDFs(u, [[u.atoms[a], u.atoms[b]] for a, b in sites], nbins=30, range=(0.0, 6.0)).run()
+    got = InterRDF_s(FrameBlock.from_atomgroup(u.atoms), sites, nbins=30, range=(0.0, 6.0)).run()
+    assert np.array_equal(got.results.count[0], want.results.count[0])
+    assert np.allclose(got.results.rdf[0], want.results.rdf[0], rtol=1e-12)
+
+
+def test_rmsd_aligntraj_contacts_classes_against_reference(mda):
+    from MDAnalysis.analysis import rms as rrms, align as ralign, contacts as rcontacts
+    from mdanalysis_b200 import FrameBlock
+    from mdanalysis_b200.analysis.rms import RMSD
+    from mdanalysis_b200.analysis.align import AlignTraj
+    from mdanalysis_b200.analysis.contacts import Contacts
+    rng = np.random.default_rng(33)
+    F, N = 12, 900
+    ref_xyz = rng.normal(0, 12, (N, 3))
+    traj = np.stack([(ref_xyz @ np.linalg.qr(rng.normal(size=(3, 3)))[0] + rng.normal(0, 4, 3)
+                      + rng.normal(0, 0.7, (N, 3))) for _ in range(F)]).astype(np.float32)
+    masses = rng.uniform(1, 32, N)
+    r = _universe(mda, ref_xyz.astype(np.float32)[None], None, masses)
+    for w in (None, "mass"):
+        u = _universe(mda, traj, None, masses)
+        want = rrms.RMSD(u, r, select="all", weights=w).run().results.rmsd
+        got = RMSD(FrameBlock.from_atomgroup(u.atoms), FrameBlock.from_atomgroup(r.atoms), weights=w).run().results.rmsd
+        assert np.allclose(got, want, rtol=1e-5, atol=0)        # north_star tolerance; observed ~1e-12
+        assert np.allclose(got[:, 2], want[:, 2], rtol=1e-9)
+        u2 = _universe(mda, traj, None, masses)
+        al = ralign.AlignTraj(u2, r, select="all", weights=w, in_memory=True).run()
+        blk = FrameBlock.from_atomgroup(_universe(mda, traj, None, masses).atoms)
+        g = AlignTraj(blk, FrameBlock.from_atomgroup(r.atoms), weights=w).run()
+        assert np.allclose(g.results.rmsd, al.results.rmsd, rtol=1e-9)
+        moved = u2.trajectory.timeseries(order="fac")
+        assert np.abs(np.asarray(blk.positions) - moved).max() <= 1.5e-4      # test_align.py:450 tolerance
+    box = np.array([60, 60, 60, 90, 90, 90], dtype=np.float32)
+    u = _universe(mda, traj + 30, np.tile(box, (F, 1)), masses)
+    gA, gB = u.atoms[:300], u.atoms[500:800]
+    u.trajectory[0]
+    for method in ("hard_cut", "soft_cut", "radius_cut"):
+        want = rcontacts.Contacts(u, select=(gA, gB), refgroup=(gA, gB), method=method, radius=8.0).run()
+        u.trajectory[0]
+        blk = FrameBlock.from_atomgroup(u.atoms)
+        refA = FrameBlock(blk.positions[:1, :300], blk.dimensions[:1])
+        refB = FrameBlock(blk.positions[:1, 500:800], blk.dimensions[:1])
+        got = Contacts(blk, select=(np.arange(300), np.arange(500, 800)), refgroup=(refA, refB), method=method,
+                       radius=8.0).run()
+        assert np.allclose(got.results.timeseries, want.results.timeseries, rtol=1e-12)
