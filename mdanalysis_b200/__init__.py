@@ -5,7 +5,7 @@ Layout
   _cabi.py     ctypes binding of that ABI
   lib/         host-side mirror of ``MDAnalysis.lib`` for the path
                (distances, nsgrid.FastNS, qcprot, mdamath, util)
-  analysis/    block-of-frames drivers: RMSD, AlignTraj, InterRDF, contacts
+  analysis/    block-of-frames drivers: RMSD, AlignTraj, InterRDF, InterRDF_s, Contacts
   frames.py    FrameBlock: [F, n, 3] float32 block of trajectory frames
   parallel.py  frame sharding over ranks + NCCL reductions (torch.distributed)
   register.py  plugs the backend into an installed MDAnalysis (``backend='cuda'``)
