@@ -2,7 +2,7 @@
 // pair search with warp-aggregated compaction, brute-force capped distances.
 // Reference: package/MDAnalysis/lib/nsgrid.pyx (cited per function) and
 // package/MDAnalysis/lib/distances.py:589-673, 1050-1130 (brute force).
-#include "engine.cuh"
+#include "rowpairs.cuh"
 
 #include <math.h>
 #include <new>
@@ -252,10 +252,36 @@ struct mdagpu_grid {
 
 namespace mdagpu {
 
+// How the search walks the grid: the row-staged kernel (rowpairs.cuh) when the per-cell-pair
+// image prediction holds for this geometry, else one thread per query with global loads.
+struct PairTraversal {
+    int row = 0;
+    RowParams rp = { 1, 1 };
+    uint64_t grid_x = 0;
+};
+
+static PairTraversal choose_traversal(int mic, const FrameGeom &fg, double cutoff, uint64_t n_queries, bool consistent)
+{
+    PairTraversal tv;
+    if (mic == MIC_ORTHO_ROUND || !consistent || fg.grid.ncell_total < 8) return tv;
+    if (!rowtile_supported(mic, fg.grid, fg.box, cutoff, 1)) return tv;
+    const double occupancy = (double)n_queries / (double)fg.grid.ncell_total;
+    const int nx = fg.grid.ncells[0];
+    int R = (int)(128.0 / fmax(occupancy, 1e-9));
+    R = R < 1 ? 1 : (R > ROW_MAXR ? ROW_MAXR : R);
+    if (R > nx) R = nx;
+    const int runs = (nx + R - 1) / R;
+    tv.rp.W = 1;
+    tv.rp.R = (nx + runs - 1) / runs;
+    tv.grid_x = (uint64_t)runs * (uint64_t)fg.grid.ncells[1] * (uint64_t)fg.grid.ncells[2];
+    tv.row = 1;
+    return tv;
+}
+
 template <int MIC, bool SELF>
 static int run_pair_search(const CellList &ql, uint64_t nq, const CellList &cl,
                            const FrameGeom *fg_dev, const SearchParams &sp, uint64_t guess,
-                           int orient, cudaStream_t st, mdagpu_pairs *res)
+                           int orient, const PairTraversal &tv, cudaStream_t st, mdagpu_pairs *res)
 {
     DevBuf counter;
     MDA_CUDA(counter.alloc(sizeof(unsigned long long), st));
@@ -268,9 +294,16 @@ static int run_pair_search(const CellList &ql, uint64_t nq, const CellList &cl,
         res->capacity = cap;
         MDA_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
         PairSink sink = { res->pairs, res->dist, counter.as<unsigned long long>(), cap, orient };
-        dim3 grid(cdiv(nq, PairSink::THREADS), 1);
-        MDA_LAUNCH_AS(SELF ? "pair_self_search" : "pair_search", (pair_search_kernel<MIC, SELF, PairSink>), grid, PairSink::THREADS, 0, st,
-                   ql.atoms(), ql.key_of_sorted(), nq, cl.atoms(), cl.start(), fg_dev, 0, sp, sink);
+        if constexpr (MIC != MIC_ORTHO_ROUND) if (tv.row) {
+            dim3 grid((unsigned)tv.grid_x, 1);
+            MDA_LAUNCH_AS(SELF ? "pair_self_search" : "pair_search", (row_pairs_kernel<MIC, SELF, PairSink>), grid, PairSink::THREADS, 0, st,
+                       ql.atoms(), ql.start(), cl.atoms(), cl.start(), fg_dev, 0, tv.rp, sp, sink);
+        }
+        if (!tv.row || MIC == MIC_ORTHO_ROUND) {
+            dim3 grid(cdiv(nq, PairSink::THREADS), 1);
+            MDA_LAUNCH_AS(SELF ? "pair_self_search" : "pair_search", (pair_search_kernel<MIC, SELF, PairSink>), grid, PairSink::THREADS, 0, st,
+                       ql.atoms(), ql.key_of_sorted(), nq, cl.atoms(), cl.start(), fg_dev, 0, sp, sink);
+        }
         MDA_CHECK_LAUNCH();
         unsigned long long found = 0;
         MDA_CUDA(cudaMemcpyAsync(&found, counter.p, sizeof(found), cudaMemcpyDeviceToHost, st));
@@ -285,13 +318,13 @@ static int run_pair_search(const CellList &ql, uint64_t nq, const CellList &cl,
 template <bool SELF>
 static int dispatch_pair_search(int mic, const CellList &ql, uint64_t nq, const CellList &cl,
                                 const FrameGeom *fg_dev, const SearchParams &sp, uint64_t guess,
-                                int orient, cudaStream_t st, mdagpu_pairs *res)
+                                int orient, const PairTraversal &tv, cudaStream_t st, mdagpu_pairs *res)
 {
     switch (mic) {
-    case MIC_NONE: return run_pair_search<MIC_NONE, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, st, res);
-    case MIC_ORTHO_ROUND: return run_pair_search<MIC_ORTHO_ROUND, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, st, res);
-    case MIC_ORTHO_LAZY: return run_pair_search<MIC_ORTHO_LAZY, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, st, res);
-    case MIC_TRICLINIC: return run_pair_search<MIC_TRICLINIC, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, st, res);
+    case MIC_NONE: return run_pair_search<MIC_NONE, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, tv, st, res);
+    case MIC_ORTHO_ROUND: return run_pair_search<MIC_ORTHO_ROUND, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, tv, st, res);
+    case MIC_ORTHO_LAZY: return run_pair_search<MIC_ORTHO_LAZY, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, tv, st, res);
+    case MIC_TRICLINIC: return run_pair_search<MIC_TRICLINIC, SELF>(ql, nq, cl, fg_dev, sp, guess, orient, tv, st, res);
     }
     return set_error(MDAGPU_ERR_INVALID, "unknown minimum-image flavour %d", mic);
 }
@@ -394,6 +427,20 @@ extern "C" int mdagpu_grid_info(const mdagpu_grid *g, int *ncells3, double *cell
 
 extern "C" void mdagpu_grid_free(mdagpu_grid *g) { delete g; }
 
+// Triclinic cells: an atom that the float64 cell arithmetic folded into a cell it does not lie
+// in (flagged by cell_key_kernel) breaks the per-cell image prediction of the row kernel.
+static int cells_consistent(int mic, const CellList &cl, const CellList *ql, cudaStream_t st, bool *ok)
+{
+    *ok = true;
+    if (mic != MIC_TRICLINIC) return MDAGPU_OK;
+    unsigned bad[2] = { 0u, 0u };
+    MDA_CUDA(cudaMemcpyAsync(&bad[0], cl.inconsistent(), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    if (ql) MDA_CUDA(cudaMemcpyAsync(&bad[1], ql->inconsistent(), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MDA_CUDA(cudaStreamSynchronize(st));
+    *ok = !(bad[0] | bad[1]);
+    return MDAGPU_OK;
+}
+
 static double grid_volume(const mdagpu_grid *g)
 {
     const GridGeom &gg = g->fg.grid;
@@ -422,8 +469,15 @@ extern "C" int mdagpu_grid_search(mdagpu_grid *g, const float *queries, uint64_t
         sp.use_filter = 1;
         sp.stencil = 1;
         sp.include_self = 0;
-        rc = dispatch_pair_search<false>(g->mic, ql, nq, g->cl, g->fg_dev, sp,
-                                         guess_pairs(nq, g->n, g->cutoff, grid_volume(g)), 0, st, res);
+        bool consistent = true;
+        rc = cells_consistent(g->mic, g->cl, &ql, st, &consistent);
+        if (rc == MDAGPU_OK) {
+            // the row kernel filters with its own, tighter error bound (rowtile_abs_err)
+            const PairTraversal tv = choose_traversal(g->mic, g->fg, g->cutoff, nq, consistent);
+            if (tv.row) sp.d2_filter = filter_threshold(sp.d2_max, rowtile_abs_err(g->mic, g->fg.box, g->cutoff));
+            rc = dispatch_pair_search<false>(g->mic, ql, nq, g->cl, g->fg_dev, sp,
+                                             guess_pairs(nq, g->n, g->cutoff, grid_volume(g)), 0, tv, st, res);
+        }
     }
     if (rc != MDAGPU_OK) { delete res; return rc; }
     *out = res;
@@ -445,8 +499,14 @@ extern "C" int mdagpu_grid_self_search(mdagpu_grid *g, mdagpu_stream_t stream, m
     sp.use_filter = 1;
     sp.stencil = 1;
     sp.include_self = 0;
-    int rc = dispatch_pair_search<true>(g->mic, g->cl, g->n, g->cl, g->fg_dev, sp,
-                                        guess_pairs(g->n, g->n, g->cutoff, grid_volume(g)) / 2 + 4096, 0, st, res);
+    bool consistent = true;
+    int rc = cells_consistent(g->mic, g->cl, nullptr, st, &consistent);
+    if (rc == MDAGPU_OK) {
+        const PairTraversal tv = choose_traversal(g->mic, g->fg, g->cutoff, g->n, consistent);
+        if (tv.row) sp.d2_filter = filter_threshold(sp.d2_max, rowtile_abs_err(g->mic, g->fg.box, g->cutoff));
+        rc = dispatch_pair_search<true>(g->mic, g->cl, g->n, g->cl, g->fg_dev, sp,
+                                        guess_pairs(g->n, g->n, g->cutoff, grid_volume(g)) / 2 + 4096, 0, tv, st, res);
+    }
     if (rc != MDAGPU_OK) { delete res; return rc; }
     *out = res;
     return MDAGPU_OK;
@@ -524,8 +584,8 @@ extern "C" int mdagpu_capped_bruteforce(const float *ref, uint64_t n, const floa
         sp.include_self = 0;
         const int mic = box_mode == BOX_ORTHO ? MIC_ORTHO_ROUND : (box_mode == BOX_TRICLINIC ? MIC_TRICLINIC : MIC_NONE);
         const uint64_t guess = (self ? n * 32 : n * 64) + 4096;
-        if (self) rc = dispatch_pair_search<true>(mic, rl, n, rl, fg_dev.as<FrameGeom>(), sp, guess, 1, st, res);
-        else rc = dispatch_pair_search<false>(mic, rl, n, cl, fg_dev.as<FrameGeom>(), sp, guess, 0, st, res);
+        if (self) rc = dispatch_pair_search<true>(mic, rl, n, rl, fg_dev.as<FrameGeom>(), sp, guess, 1, PairTraversal(), st, res);
+        else rc = dispatch_pair_search<false>(mic, rl, n, cl, fg_dev.as<FrameGeom>(), sp, guess, 0, PairTraversal(), st, res);
     }
     if (rc != MDAGPU_OK) { delete res; return rc; }
     *out = res;
