@@ -58,6 +58,9 @@ struct BoxParams {
     // in mic_ortho_round (valid because invL*dx is exact in double):
     float x_half[3];  // smallest float x with (double)invL*x >= 0.5
     float x_lim[3];   // below this |x|, |s| < 1.5 is guaranteed
+    // triclinic 8-image shortcut (mic_triclinic_fast): 1 / diagonal, tilt ratios, and the
+    // squared smallest perpendicular width of the cell (with a safety factor); 0 disables it
+    float tri_inv[3], tri_t3, tri_t6, tri_t7, tri_w2;
 };
 
 static inline BoxParams make_box_params(int mode, const float *box)
@@ -71,6 +74,7 @@ static inline BoxParams make_box_params(int mode, const float *box)
     }
     for (int k = 0; k < 9; ++k) b.h[k] = 0.0f;
     b.r0 = b.r4 = b.r8 = b.r3 = b.r6 = b.r7 = b.ay = b.az = b.bz = 0.0;
+    b.tri_inv[0] = b.tri_inv[1] = b.tri_inv[2] = b.tri_t3 = b.tri_t6 = b.tri_t7 = b.tri_w2 = 0.0f;
     if (mode == BOX_ORTHO) {
         for (int k = 0; k < 3; ++k) {
             b.L[k] = box[k];
@@ -98,6 +102,26 @@ static inline BoxParams make_box_params(int mode, const float *box)
         b.ay = (double)box[3] * b.r4;
         b.az = (double)box[6] * b.r8;
         b.bz = (double)box[7] * b.r8;
+        // perpendicular widths w_k = volume / |cross of the other two cell vectors|
+        const double a0[3] = { box[0], box[1], box[2] }, a1[3] = { box[3], box[4], box[5] }, a2[3] = { box[6], box[7], box[8] };
+        const double c12[3] = { a1[1] * a2[2] - a1[2] * a2[1], a1[2] * a2[0] - a1[0] * a2[2], a1[0] * a2[1] - a1[1] * a2[0] };
+        const double c20[3] = { a2[1] * a0[2] - a2[2] * a0[1], a2[2] * a0[0] - a2[0] * a0[2], a2[0] * a0[1] - a2[1] * a0[0] };
+        const double c01[3] = { a0[1] * a1[2] - a0[2] * a1[1], a0[2] * a1[0] - a0[0] * a1[2], a0[0] * a1[1] - a0[1] * a1[0] };
+        const double vol = fabs(a0[0] * c12[0] + a0[1] * c12[1] + a0[2] * c12[2]);
+        const double n12 = sqrt(c12[0] * c12[0] + c12[1] * c12[1] + c12[2] * c12[2]);
+        const double n20 = sqrt(c20[0] * c20[0] + c20[1] * c20[1] + c20[2] * c20[2]);
+        const double n01 = sqrt(c01[0] * c01[0] + c01[1] * c01[1] + c01[2] * c01[2]);
+        const bool sane = box[0] > 0.0f && box[4] > 0.0f && box[8] > 0.0f && box[1] == 0.0f && box[2] == 0.0f &&
+                          box[5] == 0.0f && vol > 0.0 && vol < 1e30 && n12 > 0.0 && n20 > 0.0 && n01 > 0.0;
+        if (sane) {
+            double w = vol / n12;
+            if (vol / n20 < w) w = vol / n20;
+            if (vol / n01 < w) w = vol / n01;
+            w *= 1.0 - 2e-3;
+            b.tri_inv[0] = (float)b.r0; b.tri_inv[1] = (float)b.r4; b.tri_inv[2] = (float)b.r8;
+            b.tri_t3 = box[3]; b.tri_t6 = box[6]; b.tri_t7 = box[7];
+            b.tri_w2 = (float)(w * w);
+        }
     }
     return b;
 }
@@ -233,6 +257,54 @@ MDA_HD double mic_triclinic_fast(float tx, float ty, float tz, const float *h, D
     return mic_triclinic(out, h);
 }
 
+// The same winner from EIGHT images when that is provable.  With s = d H^-1 the fractional
+// coordinates of d, image (a, b, c) has fractional coordinates (s + n) and is at least
+// w_k |s_k + n_k| long (w_k: perpendicular width of the cell along axis k).  The 19 images
+// that shift some axis the wrong way (|s_k + n_k| >= 1) are therefore >= min w_k long: if the
+// best of the other eight (n_k in {0, -sign(s_k)}) is shorter than that, it is the winner of
+// the reference's 27-image loop.  Otherwise -- and whenever the FP32 values cannot separate
+// winner and runner-up -- the exhaustive path above decides.  (A wrong sign of an s_k near
+// zero only swaps one wrong-way image for another.)
+MDA_HD double mic_triclinic_fast8(float tx, float ty, float tz, const BoxParams &bp, D3 &out)
+{
+    const float *h = bp.h;
+    if (bp.tri_w2 > 0.0f) {
+        const float sz = tz * bp.tri_inv[2];
+        const float sy = (ty - sz * bp.tri_t7) * bp.tri_inv[1];
+        const float sx = (tx - sy * bp.tri_t3 - sz * bp.tri_t6) * bp.tri_inv[0];
+        const int a1 = sx >= 0.0f ? -1 : 1, b1 = sy >= 0.0f ? -1 : 1, c1 = sz >= 0.0f ? -1 : 1;
+        float best = FLT_MAX, second = FLT_MAX;
+        int ba = 0, bb = 0, bc = 0;
+#pragma unroll
+        for (int ia = 0; ia < 2; ++ia) {
+            const int a = ia ? a1 : 0;
+            const float xa = tx + h[0] * (float)a;
+#pragma unroll
+            for (int ib = 0; ib < 2; ++ib) {
+                const int b = ib ? b1 : 0;
+                const float xab = xa + h[3] * (float)b;
+                const float yb = ty + h[4] * (float)b;
+#pragma unroll
+                for (int ic = 0; ic < 2; ++ic) {
+                    const int c = ic ? c1 : 0;
+                    const float x = xab + h[6] * (float)c;
+                    const float y = yb + h[7] * (float)c;
+                    const float z = tz + h[8] * (float)c;
+                    const float r2 = fmaf(x, x, fmaf(y, y, z * z));
+                    if (r2 < best) { second = best; best = r2; ba = a; bb = b; bc = c; }
+                    else if (r2 < second) second = r2;
+                }
+            }
+        }
+        if (best < bp.tri_w2 && second - best > 1e-4f * second) {
+            D3 d;
+            d.x = (double)tx; d.y = (double)ty; d.z = (double)tz;
+            return tric_image_d2(d, h, ba, bb, bc, out);
+        }
+    }
+    return mic_triclinic_fast(tx, ty, tz, h, out);
+}
+
 // ---- wraps -------------------------------------------------------------------
 MDA_HD float wrap_ortho_axis(float x, float L, double invL)
 {
@@ -352,7 +424,7 @@ MDA_HD double pair_d2_exact(float px, float py, float pz, float qx, float qy, fl
         return x * x + y * y + z * z;
     } else {
         D3 img;
-        return mic_triclinic_fast(tx, ty, tz, b.h, img);
+        return mic_triclinic_fast8(tx, ty, tz, b, img);
     }
 }
 

@@ -225,15 +225,21 @@ int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameG
 // ---------------------------------------------------------------------------
 }  // namespace mdagpu
 
+// Result buffers come from the stream-ordered pool (kept cached between calls, common.cuh):
+// a fresh cudaMalloc of the GB-sized lists of a 1 M-atom search costs more than the search.
 struct mdagpu_pairs {
     long long *pairs = nullptr;     // device [count][2]
     double *dist = nullptr;         // device [count]
     unsigned long long count = 0, capacity = 0;
-    ~mdagpu_pairs()
+    cudaStream_t stream = nullptr;
+    void release()
     {
-        if (pairs) cudaFree(pairs);
-        if (dist) cudaFree(dist);
+        if (pairs) cudaFreeAsync(pairs, stream);
+        if (dist) cudaFreeAsync(dist, stream);
+        pairs = nullptr;
+        dist = nullptr;
     }
+    ~mdagpu_pairs() { release(); }
 };
 
 struct mdagpu_grid {
@@ -287,10 +293,11 @@ static int run_pair_search(const CellList &ql, uint64_t nq, const CellList &cl,
     MDA_CUDA(counter.alloc(sizeof(unsigned long long), st));
     unsigned long long cap = guess < 1024 ? 1024 : guess;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if (res->pairs) { cudaFree(res->pairs); res->pairs = nullptr; }
-        if (res->dist) { cudaFree(res->dist); res->dist = nullptr; }
-        MDA_CUDA(cudaMalloc(&res->pairs, cap * 2 * sizeof(long long)));
-        MDA_CUDA(cudaMalloc(&res->dist, cap * sizeof(double)));
+        res->release();
+        res->stream = st;
+        pool_init();
+        MDA_CUDA(cudaMallocAsync(&res->pairs, cap * 2 * sizeof(long long), st));
+        MDA_CUDA(cudaMallocAsync(&res->dist, cap * sizeof(double), st));
         res->capacity = cap;
         MDA_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
         PairSink sink = { res->pairs, res->dist, counter.as<unsigned long long>(), cap, orient };

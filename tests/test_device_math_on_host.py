@@ -166,3 +166,45 @@ def test_histogram_bin_semantics(hostcheck):
         for v in d:
             got[hostcheck.hc_histogram_bin(C.c_double(v), p(edges, F64P), nbins)] += 1
         assert np.array_equal(got, want)
+
+
+def _brute27(d32, h):
+    """calc_distances.h:72-114 in NumPy: float32 difference widened, 27 images in loop order
+    (x, y, z), strict <, shifts h*i evaluated in float32."""
+    d = d32.astype(np.float64)
+    best = np.full(len(d), float(np.finfo(np.float32).max))
+    for a in (-1, 0, 1):
+        xa = d[:, 0] + np.float64(np.float32(h[0] * np.float32(a)))
+        for b in (-1, 0, 1):
+            xab = xa + np.float64(np.float32(h[3] * np.float32(b)))
+            yb = d[:, 1] + np.float64(np.float32(h[4] * np.float32(b)))
+            for c in (-1, 0, 1):
+                x = xab + np.float64(np.float32(h[6] * np.float32(c)))
+                y = yb + np.float64(np.float32(h[7] * np.float32(c)))
+                z = d[:, 2] + np.float64(np.float32(h[8] * np.float32(c)))
+                r2 = x * x + y * y + z * z
+                best = np.where(r2 < best, r2, best)
+    return best
+
+
+@pytest.mark.parametrize("dims", [[10, 10, 10, 50, 60, 70], [20, 8, 30, 100, 120, 95], [5, 40, 12, 89, 91, 120],
+                                  [30, 30, 30, 60, 60, 90], [50, 50, 50, 70.53571, 109.48542, 70.518196],
+                                  [12, 12, 12, 35, 40, 45], [9, 9, 9, 90, 90, 60]])
+@pytest.mark.parametrize("spread", [1.0, 2.5])
+def test_pair_d2_triclinic_eight_image_shortcut(oracle, hostcheck, dims, spread):
+    """The 8-image shortcut of mic_triclinic_fast8 (accepted only below the smallest
+    perpendicular width of the cell) against the exhaustive 27-image loop, on skewed cells,
+    for differences inside the cell (the distance_array case) and well outside it."""
+    rng = np.random.default_rng(int(sum(dims)))
+    box = np.array(dims, dtype=np.float32)
+    mode, bb = oracle.check_box(box)
+    h = bb.reshape(9)
+    tv = h.reshape(3, 3).astype(np.float64)
+    n = 40000
+    a = ((rng.random((n, 3)) * spread - (spread - 1) / 2) @ tv).astype(np.float32)
+    b = ((rng.random((n, 3)) * spread - (spread - 1) / 2) @ tv).astype(np.float32)
+    if spread == 1.0:
+        a, b = oracle.apply_PBC(a, box), oracle.apply_PBC(b, box)
+    d2 = np.zeros(n)
+    hostcheck.hc_pair_d2(3, p(a, F32P), p(b, F32P), C.c_uint64(n), mode, p(bb, F32P), p(d2, F64P))
+    assert np.array_equal(d2, _brute27(a - b, h))
