@@ -9,15 +9,17 @@ Layout
   frames.py    FrameBlock: [F, n, 3] float32 block of trajectory frames
   parallel.py  frame sharding over ranks + NCCL reductions (torch.distributed)
   register.py  plugs the backend into an installed MDAnalysis (``backend='cuda'``)
+  adapters.py  run_on_gpu(analysis): an MDAnalysis analysis object computed by the GPU classes
 
 There is no CPU fallback: every numerical result comes from libmdagpu.so.
 """
 from . import _cabi
 from .frames import FrameBlock
 from . import lib, analysis, parallel, register  # noqa: F401
+from .adapters import run_on_gpu
 
 __version__ = "0.1.0"
-__all__ = ["FrameBlock", "lib", "analysis", "parallel", "register", "library_path"]
+__all__ = ["FrameBlock", "lib", "analysis", "parallel", "register", "library_path", "run_on_gpu"]
 
 
 def library_path():

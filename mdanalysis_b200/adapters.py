@@ -1,0 +1,201 @@
+"""Run an already-constructed MDAnalysis analysis object on the GPU.
+
+The reference's analyses loop over frames in Python (``analysis/base.py:515-523``) and the
+classes on this path that are most worth accelerating (``InterRDF``, ``AlignTraj``,
+``Contacts``) refuse every non-serial executor (``_analysis_algorithm_is_parallelizable =
+False``, ``base.py:653-654``), so a ``BackendBase`` subclass cannot reach them.  This module
+is the caller-level plug instead: user code keeps building the reference object from
+AtomGroups exactly as before and replaces ``.run(...)`` by ``run_on_gpu(obj, ...)``::
+
+    rdf = InterRDF(ow, ow, nbins=150, range=(0, 15))       # MDAnalysis, unchanged
+    mdanalysis_b200.run_on_gpu(rdf, step=10)               # instead of rdf.run(step=10)
+    rdf.results.rdf                                        # filled as the reference fills it
+
+What happens: the frames of the AtomGroups are read in bulk (``FrameBlock.from_atomgroup`` ->
+``ReaderBase.timeseries``), the matching class of ``mdanalysis_b200.analysis`` is configured
+from the attributes the reference constructor left on the object, all frames go through the
+CUDA kernels in one call, and ``results`` / ``frames`` / ``times`` / ``n_frames`` are written
+back onto the reference object.  Supported: ``rdf.InterRDF``, ``rdf.InterRDF_s``, ``rms.RMSD``,
+``align.AlignTraj`` (in-memory trajectories), ``contacts.Contacts``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .frames import FrameBlock
+
+
+def _frames_of(analysis, start, stop, step, frames):
+    n = len(analysis._trajectory)
+    if frames is not None:
+        if not all(opt is None for opt in (start, stop, step)):
+            raise ValueError("start/stop/step cannot be combined with frames")
+        idx = np.asarray(frames)
+        return np.flatnonzero(idx) if idx.dtype == bool else idx
+    return np.arange(n)[slice(start, stop, step)]
+
+
+def _block(atomgroup, idx):
+    blk = FrameBlock.from_atomgroup(atomgroup)
+    if len(idx) != blk.n_frames or not np.array_equal(idx, np.arange(blk.n_frames)):
+        blk = blk.slice_frames(idx)
+    return blk
+
+
+def _finish(analysis, gpu):
+    analysis.n_frames = gpu.n_frames
+    analysis.frames = np.asarray(gpu.frames).copy()
+    analysis.times = np.asarray(gpu.times).copy()
+    return analysis
+
+
+def _run_interrdf(an, idx, device):
+    from .analysis.rdf import InterRDF
+    if getattr(an, "exclude_same", None) is not None:
+        raise NotImplementedError("exclude_same needs topology ids; use exclusion_block on the GPU path")
+    b1 = _block(an.g1, idx)
+    same = an.g2 is an.g1 or (len(an.g1) == len(an.g2) and np.array_equal(an.g1.indices, an.g2.indices))
+    b2 = b1 if same else _block(an.g2, idx)
+    if device:
+        b1 = b1.to_device()
+        b2 = b1 if same else b2.to_device()
+    gpu = InterRDF(b1, b2, nbins=an.rdf_settings["bins"], range=an.rdf_settings["range"], norm=an.norm,
+                   exclusion_block=an._exclusion_block).run()
+    for k in ("count", "edges", "bins", "rdf"):
+        an.results[k] = gpu.results[k]
+    an.volume_cum = gpu.volume_cum
+    return _finish(an, gpu)
+
+
+def _run_interrdf_s(an, idx, device):
+    from .analysis.rdf import InterRDF_s
+    u = an.ags[0][0].universe
+    blk = _block(u.atoms, idx)
+    if device:
+        blk = blk.to_device()
+    sites = [[a.indices, b.indices] for a, b in an.ags]
+    gpu = InterRDF_s(blk, sites, nbins=an.rdf_settings["bins"], range=an.rdf_settings["range"], norm=an.norm).run()
+    for k in ("count", "edges", "bins", "rdf", "indices"):
+        an.results[k] = gpu.results[k]
+    an.volume_cum = gpu.volume_cum
+    return _finish(an, gpu)
+
+
+def _run_rmsd(an, idx, device):
+    from .analysis.rms import RMSD
+    mob_u, ref_u = an.atomgroup.universe, an.reference.universe
+    blk = _block(mob_u.atoms, idx)
+    blk.masses = np.asarray(mob_u.atoms.masses, dtype=np.float64) if hasattr(mob_u.atoms, "masses") else None
+    cur = ref_u.trajectory.ts.frame
+    try:
+        ref_u.trajectory[an.ref_frame]
+        refblk = FrameBlock(ref_u.atoms.positions.copy()[None],
+                            masses=np.asarray(ref_u.atoms.masses, dtype=np.float64) if hasattr(ref_u.atoms, "masses") else None)
+    finally:
+        ref_u.trajectory[cur]
+    if device:
+        blk = blk.to_device()
+    groups = [{"mobile": g["mobile"].indices, "reference": g["reference"].indices}
+              for g in getattr(an, "_groupselections_atoms", [])]
+    gpu = RMSD(blk, refblk, select={"mobile": an.mobile_atoms.indices, "reference": an.ref_atoms.indices},
+               groupselections=groups or None, weights=an.weights,
+               weights_groupselections=an.weights_groupselections, tol_mass=an.tol_mass, ref_frame=0).run()
+    an.results.rmsd = gpu.results.rmsd
+    return _finish(an, gpu)
+
+
+def _run_aligntraj(an, idx, device):
+    from .analysis.align import AlignTraj
+    if an.filename is not None:
+        raise NotImplementedError("AlignTraj on the GPU path rewrites an in-memory trajectory (in_memory=True)")
+    mob_u, ref_u = an.mobile.universe, an.ref_atoms.universe
+    traj = mob_u.trajectory
+    arr = traj.get_array()                                   # MemoryReader: the coordinates themselves
+    order = traj.stored_order
+    blk = _block(mob_u.atoms, idx)
+    refblk = FrameBlock(ref_u.atoms.positions.copy()[None])
+    if device:
+        blk = blk.to_device()
+    w = an._weights
+    gpu = AlignTraj(blk, refblk, select={"mobile": an.mobile_atoms.indices, "reference": an.ref_atoms.indices},
+                    weights=None if w is None else np.asarray(w, dtype=np.float64), in_memory=True).run()
+    moved = gpu.results.positions
+    moved = moved.detach().cpu().numpy() if hasattr(moved, "detach") else np.asarray(moved)
+    view = np.transpose(arr, [order.find(c) for c in "fac"])      # [F, n, 3] view of the reader's array
+    view[idx] = moved
+    an.results.rmsd = np.asarray(gpu.results.rmsd)
+    return _finish(an, gpu)
+
+
+def _run_contacts(an, idx, device):
+    from .analysis.contacts import pair_list_distances
+    A, B = _block(an.grA, idx), _block(an.grB, idx)
+    dims = A.dimensions if an.pbc else None
+    Ap, Bp = (A.to_device().positions, B.to_device().positions) if device else (A.positions, B.positions)
+    ts = np.empty((A.n_frames, len(an.r0) + 1))
+    ts[:, 0] = A.frames
+    for k, (mask, r0) in enumerate(zip(an.initial_contacts, an.r0), 1):
+        ii, jj = np.nonzero(mask)                                 # row-major: the order of d[mask]
+        r = pair_list_distances(Ap, Bp, ii, jj, dims)
+        r = r.detach().cpu().numpy() if hasattr(r, "detach") else r
+        r0s = r0[mask]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            for f in range(A.n_frames):
+                ts[f, k] = an.fraction_contacts(r[f], r0s, **an.fraction_kwargs)
+    an.results.timeseries = ts
+    an.n_frames = A.n_frames
+    an.frames = np.asarray(A.frames).copy()
+    an.times = np.asarray(A.times).copy()
+    return an
+
+
+_RUNNERS = {"InterRDF": _run_interrdf, "InterRDF_s": _run_interrdf_s, "RMSD": _run_rmsd,
+            "AlignTraj": _run_aligntraj, "Contacts": _run_contacts}
+
+
+def run_on_gpu(analysis, start=None, stop=None, step=None, frames=None, device=True):
+    """``analysis.run(start, stop, step, frames)`` for a supported MDAnalysis analysis object,
+    computed by the CUDA backend.  Returns ``analysis`` with ``results`` filled.
+
+    device=True keeps the frame block on the GPU for the whole run (one H2D copy); False hands
+    host arrays to the C ABI (which streams them through its upload ring).
+    """
+    name = type(analysis).__name__
+    runner = _RUNNERS.get(name)
+    if runner is None or not type(analysis).__module__.startswith("MDAnalysis.analysis"):
+        raise TypeError(f"run_on_gpu(): no GPU path for {type(analysis).__module__}.{name}; "
+                        f"supported: {sorted(_RUNNERS)}")
+    idx = _frames_of(analysis, start, stop, step, frames)
+    return runner(analysis, idx, device)
+
+
+def cuda_backend(n_workers: int = 1):
+    """A ``BackendBase`` executor for ``AnalysisBase.run(backend=..., unsupported_backend=True)``
+    (``analysis/backends.py:43-157``, ``analysis/base.py:590-695``).
+
+    ``apply(func, computations)`` receives ``func = partial(analysis._compute, ...)`` and one
+    ``[(result index, frame number), ...]`` array per part; each part is computed by
+    ``run_on_gpu`` on a shallow copy of the analysis object, which then carries ``frames``,
+    ``times`` and ``results`` for the reference's own aggregation (``_get_aggregator``,
+    ``ResultsGroup.merge``).  Only classes that declare themselves parallelizable get this far
+    in the reference (``RMSD`` on this path); for the others use ``run_on_gpu`` directly.
+    """
+    import copy
+
+    from MDAnalysis.analysis.backends import BackendBase
+    from MDAnalysis.analysis.results import Results
+
+    class CudaBackend(BackendBase):
+        def apply(self, func, computations):
+            analysis = getattr(getattr(func, "func", func), "__self__", None)
+            if analysis is None:
+                raise ValueError("CudaBackend.apply: expected a bound AnalysisBase._compute")
+            out = []
+            for indexed_frames in computations:
+                part = copy.copy(analysis)
+                part.results = Results()
+                frames = np.asarray(indexed_frames)[:, 1] if len(indexed_frames) else np.empty(0, dtype=int)
+                out.append(run_on_gpu(part, frames=frames))
+            return out
+
+    return CudaBackend(n_workers=n_workers)

@@ -154,3 +154,84 @@ def test_rmsd_aligntraj_contacts_classes_against_reference(mda):
         got = Contacts(blk, select=(np.arange(300), np.arange(500, 800)), refgroup=(refA, refB), method=method,
                        radius=8.0).run()
         assert np.allclose(got.results.timeseries, want.results.timeseries, rtol=1e-12)
+
+
+def test_run_on_gpu_fills_reference_objects(mda):
+    """mdanalysis_b200.run_on_gpu(obj) in place of obj.run(): the reference objects, built from
+    AtomGroups as usual, end up with the results the reference computes itself."""
+    from MDAnalysis.analysis.rdf import InterRDF, InterRDF_s
+    from MDAnalysis.analysis import rms as rrms, align as ralign, contacts as rcontacts
+    from mdanalysis_b200 import run_on_gpu
+    rng = np.random.default_rng(77)
+    F, N = 8, 1200
+    box = np.array([36, 33, 30, 90, 90, 90], dtype=np.float32)
+    pos = (rng.random((F, N, 3)) * box[:3]).astype(np.float32)
+    masses = rng.uniform(1, 32, N)
+    dims = np.tile(box, (F, 1))
+    u = _universe(mda, pos, dims, masses)
+    # InterRDF, with a frame stride and an exclusion block
+    for kw, run_kw in (({}, {}), ({"exclusion_block": (4, 4)}, {"step": 2}), ({"norm": "none"}, {"start": 1, "stop": 6})):
+        want = InterRDF(u.atoms[:600], u.atoms[400:], nbins=60, range=(0.0, 9.0), **kw).run(**run_kw)
+        got = run_on_gpu(InterRDF(u.atoms[:600], u.atoms[400:], nbins=60, range=(0.0, 9.0), **kw), **run_kw)
+        assert np.array_equal(got.results.count, want.results.count)
+        assert np.allclose(got.results.rdf, want.results.rdf, rtol=1e-12)
+        assert np.array_equal(got.frames, want.frames) and got.n_frames == want.n_frames
+    ags = [[u.atoms[[1, 2]], u.atoms[100:300]]]
+    want = InterRDF_s(u, ags, nbins=25, range=(0.0, 7.0)).run()
+    got = run_on_gpu(InterRDF_s(u, ags, nbins=25, range=(0.0, 7.0)))
+    assert np.array_equal(got.results.count[0], want.results.count[0])
+    assert np.allclose(got.results.rdf[0], want.results.rdf[0], rtol=1e-12)
+    assert np.allclose(got.get_cdf()[0], want.get_cdf()[0], rtol=1e-12)
+    # RMSD with a sub-selection, group selections and mass weights
+    ref_xyz = rng.normal(0, 10, (N, 3))
+    traj = np.stack([(ref_xyz @ np.linalg.qr(rng.normal(size=(3, 3)))[0] + rng.normal(0, 3, 3)
+                      + rng.normal(0, 0.6, (N, 3))) for _ in range(F)]).astype(np.float32)
+    r = _universe(mda, ref_xyz.astype(np.float32)[None], None, masses)
+    kw = dict(select="index 0:799", groupselections=["index 800:999", "index 1000:1199"], weights="mass")
+    want = rrms.RMSD(_universe(mda, traj, None, masses), r, **kw).run(step=2)
+    got = run_on_gpu(rrms.RMSD(_universe(mda, traj, None, masses), r, **kw), step=2)
+    assert np.allclose(got.results.rmsd, want.results.rmsd, rtol=1e-6, atol=0)
+    # AlignTraj rewrites the in-memory trajectory
+    u_ref, u_gpu = _universe(mda, traj, None, masses), _universe(mda, traj, None, masses)
+    want = ralign.AlignTraj(u_ref, r, select="index 0:599", in_memory=True).run()
+    got = run_on_gpu(ralign.AlignTraj(u_gpu, r, select="index 0:599", in_memory=True))
+    assert np.allclose(got.results.rmsd, want.results.rmsd, rtol=1e-9)
+    assert np.abs(u_gpu.trajectory.timeseries(order="fac") - u_ref.trajectory.timeseries(order="fac")).max() <= 1.5e-4
+    u_gpu.trajectory[3]
+    u_ref.trajectory[3]
+    assert np.abs(u_gpu.atoms.positions - u_ref.atoms.positions).max() <= 1.5e-4
+    # Contacts with the soft cut-off
+    uc = _universe(mda, traj + 25, np.tile(np.array([55, 55, 55, 90, 90, 90], dtype=np.float32), (F, 1)), masses)
+    gA, gB = uc.atoms[:300], uc.atoms[700:1000]
+    for method in ("hard_cut", "soft_cut", "radius_cut"):
+        uc.trajectory[0]
+        want = rcontacts.Contacts(uc, select=(gA, gB), refgroup=(gA, gB), method=method, radius=9.0).run()
+        uc.trajectory[0]
+        got = run_on_gpu(rcontacts.Contacts(uc, select=(gA, gB), refgroup=(gA, gB), method=method, radius=9.0))
+        assert np.allclose(got.results.timeseries, want.results.timeseries, rtol=1e-12)
+    with pytest.raises(TypeError, match="no GPU path"):
+        run_on_gpu(object())
+
+
+def test_cuda_backend_executor_for_analysisbase_run(mda):
+    """Plug point 4: RMSD.run(backend=CudaBackend, unsupported_backend=True) -- the reference's own
+    run() splits the frames, our executor computes each part on the GPU, the reference's
+    aggregator (ndarray_vstack) merges them."""
+    from MDAnalysis.analysis import rms as rrms
+    from MDAnalysis.analysis.rdf import InterRDF
+    from mdanalysis_b200.adapters import cuda_backend
+    rng = np.random.default_rng(4)
+    F, N = 10, 500
+    ref_xyz = rng.normal(0, 10, (N, 3))
+    traj = np.stack([(ref_xyz + rng.normal(0, 0.8, (N, 3))) for _ in range(F)]).astype(np.float32)
+    masses = rng.uniform(1, 32, N)
+    r = _universe(mda, ref_xyz.astype(np.float32)[None], None, masses)
+    want = rrms.RMSD(_universe(mda, traj, None, masses), r, select="all").run()
+    for parts in (1, 3):
+        got = rrms.RMSD(_universe(mda, traj, None, masses), r, select="all").run(
+            backend=cuda_backend(n_workers=parts), n_parts=parts, unsupported_backend=True)
+        assert np.allclose(got.results.rmsd, want.results.rmsd, rtol=1e-9, atol=0)
+        assert np.array_equal(got.frames, want.frames)
+    u = _universe(mda, traj, np.tile(np.array([80, 80, 80, 90, 90, 90], dtype=np.float32), (F, 1)), masses)
+    with pytest.raises(ValueError):                  # the reference itself refuses: not parallelizable
+        InterRDF(u.atoms, u.atoms).run(backend=cuda_backend(), unsupported_backend=True)
