@@ -353,7 +353,7 @@ struct QcpStreamParams {
 };
 
 template <bool WEIGHTED, int QS_STAGES>
-__global__ void __launch_bounds__(QS_THREADS, 1) qcp_stream_kernel(const QcpStreamParams p)
+__global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const QcpStreamParams p)
 {
     extern __shared__ __align__(128) unsigned char qs_smem[];
     __shared__ uint64_t full_bar[QS_STAGES], empty_bar[QS_STAGES];
@@ -399,20 +399,23 @@ __global__ void __launch_bounds__(QS_THREADS, 1) qcp_stream_kernel(const QcpStre
             bulk_g2s(st + FRAME_OFF + g * QS_FRAME_BYTES, p.traj + ((f0 + g) * p.natoms + (uint64_t)cc * QS_CH) * 3,
                      fbytes, &full_bar[s]);
     };
-    // after every consumed chunk: warp 0 waits until all warps have released the stage, then refills it
+    // after every consumed chunk a warp releases the stage; the PRODUCER WARP (the extra, 17th
+    // warp) waits until all consumer warps have done so and refills it -- no consumer ever
+    // blocks on another consumer (with a consumer doing the refills its own group fell behind
+    // by one chunk per stage and everybody queued up behind it)
     auto release_and_refill = [&](uint32_t k) {
         __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[k % QS_STAGES]);
+    };
+    if (warp == QS_THREADS / 32) {
         if (lane == 0) {
-            const int s = k % QS_STAGES;
-            mbar_arrive(&empty_bar[s]);
-            if (warp == 0 && (uint64_t)k + QS_STAGES < my_chunks) {
-                mbar_wait(&empty_bar[s], (k / QS_STAGES) & 1u);
-                issue((uint64_t)k + QS_STAGES);
+            for (uint64_t k = 0; k < my_chunks; ++k) {
+                if (k >= QS_STAGES) mbar_wait(&empty_bar[k % QS_STAGES], ((k - QS_STAGES) / QS_STAGES) & 1u);
+                issue(k);
             }
         }
-    };
-    if (tid == 0)
-        for (uint64_t k = 0; k < QS_STAGES && k < my_chunks; ++k) issue(k);
+        return;
+    }
 
     // ---------------- consumers ----------------
     const int g = warp / (QS_GT / 32), gt = tid % QS_GT;
@@ -690,11 +693,11 @@ extern "C" int mdagpu_qcp_trajectory(const float *traj, uint64_t nframes, uint64
         if (weights) {
             const size_t smem = 2 * (size_t)(QS_REF_BYTES + QS_W_BYTES + QS_FB * QS_FRAME_BYTES);
             MDA_CUDA(cudaFuncSetAttribute(qcp_stream_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<true, 2>), grid, QS_THREADS, smem, st, qp);
+            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<true, 2>), grid, QS_THREADS + 32, smem, st, qp);
         } else {
             const size_t smem = 3 * (size_t)(QS_REF_BYTES + QS_FB * QS_FRAME_BYTES);
             MDA_CUDA(cudaFuncSetAttribute(qcp_stream_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<false, 3>), grid, QS_THREADS, smem, st, qp);
+            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<false, 3>), grid, QS_THREADS + 32, smem, st, qp);
         }
         MDA_CHECK_LAUNCH();
         MDA_CUDA(rm.finish());
