@@ -328,17 +328,28 @@ def secondary_benchmarks(torch, hbm_peak, peak_kind, quick):
     from mdanalysis_b200.lib.mdamath import triclinic_vectors
     tv = torch.as_tensor(triclinic_vectors(box).astype(np.float64), device=dev)
     pts = (torch.rand((nn, 3), generator=g, device=dev, dtype=torch.float64) @ tv).to(torch.float32).contiguous()
+    res = FastNS(8.0, pts, box).self_search()          # warm-up: module load, result pool growth
+    del res
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    grid = FastNS(8.0, pts, box)
-    torch.cuda.synchronize()
-    t_build = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    res = grid.self_search()
-    npairs = len(res)
-    t_search = time.perf_counter() - t0
-    out["fastns_self_search"] = {"atoms": nn, "pairs": npairs, "build_ms": t_build * 1e3, "search_ms": t_search * 1e3,
-                                 "pairs_per_s": npairs / t_search, "note": "wall clock incl. result allocation"}
+    best_build = best_search = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        grid = FastNS(8.0, pts, box)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        res = grid.self_search()
+        npairs = len(res)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        best_build, best_search = min(best_build, t1 - t0), min(best_search, t2 - t1)
+        del res
+    out["fastns_self_search"] = {"atoms": nn, "pairs": npairs, "build_ms": best_build * 1e3,
+                                 "search_ms": best_search * 1e3, "pairs_per_s": npairs / best_search,
+                                 "roofline": {"bound": "hbm", "achieved": npairs * 24 / best_search / 1e9, "peak": hbm_peak,
+                                              "unit": "GB/s", "frac": npairs * 24 / best_search / 1e9 / hbm_peak,
+                                              "peak_kind": peak_kind,
+                                              "note": "24 B written per pair; the search itself is FP32/FP64 pipe bound"},
+                                 "note": "wall clock of the call (result buffers from the stream-ordered pool), best of 3"}
     del res, grid, pts
     torch.cuda.empty_cache()
 

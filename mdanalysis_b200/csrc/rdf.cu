@@ -254,12 +254,28 @@ static int launch_hist(const CellList &ql, const CellList &cl, const FrameGeom *
                        const Sink &sink, size_t smem, cudaStream_t st)
 {
     dim3 grid((unsigned)tv.grid_x, (unsigned)nframes);
+    if constexpr (Sink::THREADS == 224) {
+        // the 224-thread sink exists for the packed kernel only (a whole row of home cells per CTA)
+        if constexpr (MIC == MIC_ORTHO_LAZY) {
+            if (tv.row && tv.quad) {
+                auto kern = row_quad_kernel<SELF, Sink, WQ_CAP_224, 4>;
+                const size_t total = ((smem + 15) & ~(size_t)15) + 3 * (size_t)WQ_CAP_224 * sizeof(float);
+                MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+                MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, total, st, ql.atoms(), ql.start(),
+                              cl.atoms(), cl.start(), fg_dev, per_frame, tv.rp, sp, sink);
+                MDA_CHECK_LAUNCH();
+                return MDAGPU_OK;
+            }
+        }
+        return set_error(MDAGPU_ERR_INVALID, "internal: 224-thread histogram sink without the packed kernel");
+    } else {
     if constexpr (MIC == MIC_ORTHO_LAZY && std::is_same<Sink, HistSink<128, false>>::value) {
         if (tv.row && tv.quad) {
-            auto kern = row_quad_kernel<SELF, Sink>;
-            if (smem > 24 * 1024)
-                MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, smem, st, ql.atoms(), ql.start(),
+            auto kern = row_quad_kernel<SELF, Sink, WQ_CAP_128, 7>;
+            const size_t total = ((smem + 15) & ~(size_t)15) + 3 * (size_t)WQ_CAP_128 * sizeof(float);
+            if (total > 24 * 1024)
+                MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+            MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, total, st, ql.atoms(), ql.start(),
                           cl.atoms(), cl.start(), fg_dev, per_frame, tv.rp, sp, sink);
             MDA_CHECK_LAUNCH();
             return MDAGPU_OK;
@@ -280,6 +296,7 @@ static int launch_hist(const CellList &ql, const CellList &cl, const FrameGeom *
     }
     MDA_CHECK_LAUNCH();
     return MDAGPU_OK;
+    }
 }
 
 template <class Sink>
@@ -579,6 +596,10 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             int nx_max = 0;
             for (uint64_t f = boxes_per_frame ? f0 : 0; f < (boxes_per_frame ? f0 + fc : 1); ++f)
                 nx_max = fgs[f].grid.ncells[0] > nx_max ? fgs[f].grid.ncells[0] : nx_max;
+            // packed kernel: a 224-thread CTA takes the whole row of home cells when its queries fit
+            // (no idle fourth warp in the short runs, one staging group, fewer staged cells per query)
+            if (quad && nx_max <= ROW_MAXR && (double)nx_max * occupancy <= 208.0
+                && (size_t)nbins * 7 * sizeof(uint32_t) <= 64 * 1024) threads = 224;
             int R = (int)((double)threads / fmax(occupancy, 1e-9));
             R = R < 1 ? 1 : (R > ROW_MAXR ? ROW_MAXR : R);
             if (R > nx_max) R = nx_max;
@@ -628,7 +649,8 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             else if (threads == 128) RUN_HIST(HistSink<128 COMMA true>);
             else RUN_HIST(HistSink<64 COMMA true>);
         } else {
-            if (threads == 192) RUN_HIST(HistSink<192 COMMA false>);
+            if (threads == 224) RUN_HIST(HistSink<224 COMMA false>);
+            else if (threads == 192) RUN_HIST(HistSink<192 COMMA false>);
             else if (threads == 128) RUN_HIST(HistSink<128 COMMA false>);
             else RUN_HIST(HistSink<64 COMMA false>);
         }

@@ -34,7 +34,8 @@
 
 namespace mdagpu {
 
-constexpr int WQ_CAP = 1280;              // padded candidates the tile holds (30 kB: 13 rows of a liquid)
+constexpr int WQ_CAP_128 = 1280;          // padded candidates the tile holds: 128-thread CTAs (15 kB, 7 CTAs/SM)
+constexpr int WQ_CAP_224 = 3456;          // 224-thread CTAs own a whole row of home cells (41 kB: 13 rows of C2 at once)
 constexpr int WQ_SLOW = 48;               // queued exact evaluations per warp
 constexpr float QUAD_FAR = 1.0e18f;       // sentinel coordinate: (2e18)^2 * 3 is finite in FP32
 
@@ -76,15 +77,15 @@ __device__ __forceinline__ QuadPad quad_pad(const RowInfo &ri)
 }
 
 // Walks quads [qa, qe) of one staged run for one query.  `planes` is the shared-memory
-// address of the x plane of the buffer (y and z follow at WQ_CAP floats each).  HOME: only candidates whose tile position
+// address of the x plane of the buffer (y and z follow at CAP floats each).  HOME: only candidates whose tile position
 // is behind the query's own (`ahead` = own position - position of quad qa).  Pairs inside
 // a decision band are handed to slow_fn(quad, k).
-template <bool HOME, class SlowFn>
+template <bool HOME, int CAP, class SlowFn>
 __device__ __forceinline__ void quad_walk(uint32_t planes, uint32_t qa, uint32_t qe,
                                           float nqx, float nqy, float nqz, int ahead,
                                           const QuadConst &kc, SlowFn slow_fn)
 {
-    constexpr uint32_t PL = WQ_CAP * 4;           // bytes between the planes
+    constexpr uint32_t PL = CAP * 4;              // bytes between the planes
     const float2 nqx2 = make_float2(nqx, nqx), nqy2 = make_float2(nqy, nqy), nqz2 = make_float2(nqz, nqz);
     const float2 inv2 = make_float2(kc.inv_dr, kc.inv_dr), c02 = make_float2(kc.c0, kc.c0);
     const float2 magic2 = make_float2(12582912.0f, 12582912.0f), nmagic2 = make_float2(-12582912.0f, -12582912.0f);
@@ -197,8 +198,8 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <bool SELF, class Sink>
-__global__ void __launch_bounds__(Sink::THREADS, 7)
+template <bool SELF, class Sink, int CAP, int MIN_CTAS>
+__global__ void __launch_bounds__(Sink::THREADS, MIN_CTAS)
 row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
                 const float4 *__restrict__ c_atoms, const uint32_t *__restrict__ c_start,
                 const FrameGeom *__restrict__ fgs, int per_frame, RowParams rp, SearchParams sp, Sink sink)
@@ -206,7 +207,9 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
     constexpr int T = Sink::THREADS, NW = T / 32;
     constexpr int MIC = MIC_ORTHO_LAZY;
     __shared__ RowBook bk;
-    __shared__ __align__(16) float tile[3][WQ_CAP];                // x, y, z planes of the staged rows
+    // x, y, z planes of the staged rows: dynamic shared memory behind the per-warp histograms
+    extern __shared__ __align__(16) unsigned char quad_dyn[];
+    float *tile = reinterpret_cast<float *>(quad_dyn + (((size_t)sink.nbins * NW * sizeof(uint32_t) + 15) & ~(size_t)15));
     __shared__ uint32_t s_base[ROW_MAXROWS + 1];                   // padded tile coordinate where each row starts
     __shared__ uint4 s_pad[ROW_MAXROWS];                           // {P1, P2, P3, -}: padded starts of runs 1, 2 and the row's end
     __shared__ float2 s_shift[ROW_MAXROWS];                        // the row's lattice translation (y, z)
@@ -244,7 +247,7 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
     kc.trash = smem_u32(&s_trash[tid]);
     uint2 *slowq = s_slow[warp];
     uint32_t *nslow = &s_nslow[warp];
-    const uint32_t tile0 = smem_u32(&tile[0][0]);
+    const uint32_t tile0 = smem_u32(tile);
 
     // evaluates the queued pairs, 32 at a time (all lanes of the warp)
     auto drain = [&]() {
@@ -260,7 +263,7 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
     };
 
     // Rows are staged in groups [r0, r1) that fit the tile (all of them at once for a
-    // liquid-like density); a row longer than the tile is staged in pieces [c0, c0 + WQ_CAP).
+    // liquid-like density); a row longer than the tile is staged in pieces [c0, c0 + CAP).
     int r0 = 0;
     uint32_t c0 = 0;
     while (r0 < nrows) {
@@ -269,13 +272,13 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
         uint32_t fill = 0, piece = 0;                              // piece != 0: only [c0, c0 + piece) of row r0
         {
             const uint32_t len0 = s_pad[r0].z - c0;
-            if (len0 > (uint32_t)WQ_CAP) { piece = WQ_CAP; fill = WQ_CAP; r1 = r0 + 1; }
+            if (len0 > (uint32_t)CAP) { piece = CAP; fill = CAP; r1 = r0 + 1; }
             else {
                 piece = c0 ? len0 : 0u;
                 fill = len0; r1 = r0 + 1;
                 while (r1 < nrows && !c0) {
                     const uint32_t len = s_pad[r1].z;
-                    if (fill + len > (uint32_t)WQ_CAP) break;
+                    if (fill + len > (uint32_t)CAP) break;
                     fill += len; ++r1;
                 }
             }
@@ -306,12 +309,12 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
                     if (k < n) {
                         const float *src = reinterpret_cast<const float *>(c_atoms) + 4ull * (g + k);
                         cp_async4(dst, src);
-                        cp_async4(dst + WQ_CAP * 4u, src + 1);
-                        cp_async4(dst + 2u * WQ_CAP * 4u, src + 2);
+                        cp_async4(dst + CAP * 4u, src + 1);
+                        cp_async4(dst + 2u * CAP * 4u, src + 2);
                     } else {
                         asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(QUAD_FAR) : "memory");
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + WQ_CAP * 4u), "f"(QUAD_FAR) : "memory");
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 2u * WQ_CAP * 4u), "f"(QUAD_FAR) : "memory");
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + CAP * 4u), "f"(QUAD_FAR) : "memory");
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 2u * CAP * 4u), "f"(QUAD_FAR) : "memory");
                     }
                 }
             }
@@ -368,9 +371,9 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
                         // home row, in-range run: only candidates behind the query itself
                         // (padded == row coordinate there: the left run of a home row is empty)
                         if (home && s == 1)
-                            quad_walk<true>(planes, qa, qe, -qx, -qy, -qz, (int)mypos - (int)(p_lo + 4u * qa), kc, slow_fn);
+                            quad_walk<true, CAP>(planes, qa, qe, -qx, -qy, -qz, (int)mypos - (int)(p_lo + 4u * qa), kc, slow_fn);
                         else
-                            quad_walk<false>(planes, qa, qe, -qx, -qy, -qz, 0, kc, slow_fn);
+                            quad_walk<false, CAP>(planes, qa, qe, -qx, -qy, -qz, 0, kc, slow_fn);
                     }
                 }
             }
