@@ -350,7 +350,7 @@ def secondary_benchmarks(torch, hbm_peak, peak_kind, quick):
                                               "peak_kind": peak_kind,
                                               "note": "24 B written per pair; the search itself is FP32/FP64 pipe bound"},
                                  "note": "wall clock of the call (result buffers from the stream-ordered pool), best of 3"}
-    del res, grid, pts
+    del grid, pts
     torch.cuda.empty_cache()
 
     # C5: fused contacts, 100k atoms, 8 A
