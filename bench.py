@@ -105,9 +105,9 @@ class ClockSampler:
 
 def ncu_traffic(n_frames, n_atoms):
     """DRAM bytes per launch of the pair-histogram kernel from the committed ncu capture
-    (profiles/r01e_traffic.json), scaled to this run's frames x atoms; None without it."""
+    (profiles/rdf_kernel_traffic.json), scaled to this run's frames x atoms; None without it."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "rdf_kernel_traffic.json")) as fh:
             t = json.load(fh)
         per_atom = (t["dram_bytes_read"] + t["dram_bytes_write"]) / (t["frames_per_launch"] * t["atoms"])
         return {"dram_bytes_per_launch": per_atom * n_frames * n_atoms, "unit": "B",
