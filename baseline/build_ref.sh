@@ -29,4 +29,20 @@ printf 'class InterProcessLock:\n    def __init__(self, *a, **k): pass\n    def 
 printf 'class Unpacker:\n    def __init__(self, *a, **k): raise NotImplementedError\nclass Packer:\n    def __init__(self, *a, **k): raise NotImplementedError\n' > "$HERE/_ref/mda_xdrlib/xdrlib.py"
 : > "$HERE/_ref/matplotlib/__init__.py"
 : > "$HERE/_ref/matplotlib/pyplot.py"
+# the reference's own tests for the hot path: the MDAnalysisTests package (python files) and the
+# ~19 MB of data files those test modules load; used by tests/test_gpu_reference_testsuite.py
+TS="$REF/testsuite/MDAnalysisTests"
+if [ -d "$TS" ]; then
+  mkdir -p "$HERE/_ref/MDAnalysisTests/data"
+  (cd "$TS" && find . -name '*.py' -not -path './data/*' | while read f; do mkdir -p "$HERE/_ref/MDAnalysisTests/$(dirname "$f")"; cp "$f" "$HERE/_ref/MDAnalysisTests/$f"; done)
+  [ -f "$TS/data/__init__.py" ] && cp "$TS/data/__init__.py" "$HERE/_ref/MDAnalysisTests/data/"
+  for f in analysis/align_bound.pdb.gz analysis/align_unbound.pdb.gz adk_open.crd adk_dims.dcd test.fasta adk_oplsaa.gro \
+           analysis/YiiP_lipids.gro.gz martini_dppc_chol_bilayer.gro adk_oplsaa.pdb A6PA6_alpha.pdb cobrotoxin.pdb adk.psf \
+           surface.pdb.bz2 surface.trr adk_oplsaa.tpr adk_oplsaa.xtc analysis/YiiP_lipids.xtc contacts/2F4K_qlist5_remap.dat \
+           contacts/villin_folded.gro.bz2 contacts/villin_unfolded.gro.bz2 adk_oplsaa_CA_rmsf.npy two_water_gro.gro \
+           tip125_tric_C36.psf tip125_tric_C36.dcd dppc_vesicle_hg.gro adk_open.pdb; do
+    mkdir -p "$HERE/_ref/MDAnalysisTests/data/$(dirname "$f")"
+    cp "$TS/data/$f" "$HERE/_ref/MDAnalysisTests/data/$f"
+  done
+fi
 PYTHONPATH="$HERE/_ref" python -W ignore -c "import MDAnalysis, MDAnalysis.lib.distances as d; print('baseline/_ref: MDAnalysis', MDAnalysis.__version__, list(d._distances))"

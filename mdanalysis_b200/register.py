@@ -17,12 +17,17 @@ functions for wrappers that keep the reference signature and add ``backend=``.
 from __future__ import annotations
 
 
-def install(patch_capped: bool = False, masquerade: str | None = None):
+def install(patch_capped: bool = False, masquerade=None, capped_default: str = "serial",
+            patch_classes: bool = False):
     """Register ``backend='cuda'`` with MDAnalysis.  Returns the patched module.
 
-    masquerade  also install the module under an existing key (e.g. ``'serial'``)
-                so that the reference's own parametrised tests exercise the GPU
-                (option a).
+    masquerade      also install the module under existing key(s) (``'serial'``, or a list like
+                    ``['serial', 'openmp']``) so that the reference's own parametrised tests
+                    exercise the GPU (option a).
+    capped_default  default ``backend=`` of the patched ``capped_distance`` wrappers.
+    patch_classes   also point ``MDAnalysis.lib.nsgrid.FastNS`` and
+                    ``MDAnalysis.lib.qcprot.CalcRMSDRotationalMatrix`` at the GPU twins (what the
+                    reference's ``test_nsgrid.py`` / ``test_qcprot.py`` / ``analysis.rms`` call).
     """
     import MDAnalysis.lib.distances as mda_distances
 
@@ -30,14 +35,21 @@ def install(patch_capped: bool = False, masquerade: str | None = None):
     from .lib import distances as gpu_distances
 
     mda_distances._distances["cuda"] = c_distances_cuda
-    if masquerade:
-        mda_distances._distances[masquerade] = c_distances_cuda
+    for key in ([masquerade] if isinstance(masquerade, str) else (masquerade or [])):
+        mda_distances._distances[key] = c_distances_cuda
+    if patch_classes:
+        import MDAnalysis.lib.nsgrid as mda_nsgrid
+        import MDAnalysis.lib.qcprot as mda_qcprot
+        from .lib import nsgrid as gpu_nsgrid
+        from .lib import qcprot as gpu_qcprot
+        mda_nsgrid.FastNS = gpu_nsgrid.FastNS
+        mda_qcprot.CalcRMSDRotationalMatrix = gpu_qcprot.CalcRMSDRotationalMatrix
     if patch_capped:
         ref_capped = mda_distances.capped_distance
         ref_self_capped = mda_distances.self_capped_distance
 
         def capped_distance(reference, configuration, max_cutoff, min_cutoff=None, box=None,
-                            method=None, return_distances=True, backend="serial"):
+                            method=None, return_distances=True, backend=capped_default):
             if backend.lower() == "cuda":
                 return gpu_distances.capped_distance(reference, configuration, max_cutoff,
                                                      min_cutoff=min_cutoff, box=box, method=method,
@@ -46,7 +58,7 @@ def install(patch_capped: bool = False, masquerade: str | None = None):
                               method=method, return_distances=return_distances)
 
         def self_capped_distance(reference, max_cutoff, min_cutoff=None, box=None, method=None,
-                                 return_distances=True, backend="serial"):
+                                 return_distances=True, backend=capped_default):
             if backend.lower() == "cuda":
                 return gpu_distances.self_capped_distance(reference, max_cutoff,
                                                           min_cutoff=min_cutoff, box=box,
