@@ -300,6 +300,38 @@ def secondary_benchmarks(torch, hbm_peak, peak_kind, quick):
         out[f"self_distance_array_{name}"] = {"pairs_per_s": pairs / ms * 1e3, "ms": ms,
                                               "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                                            "frac": gbs / hbm_peak, "peak_kind": peak_kind}}
+    # C1 as a user calls it: one frame pair through the NumPy front end (host arrays in, host array out),
+    # beside the reference's own C kernels (oracle/_ref: calc_distances.h compiled as the reference builds
+    # it) on one host core and, for the OpenMP build, on all of them
+    try:
+        from oracle import oracle as orc
+        orc.build()
+        x0, x1 = xyz[0].cpu().numpy(), xyz[1].cpu().numpy()
+        box6 = {"none": None, "ortho": np.array([50, 50, 50, 90, 90, 90], dtype=np.float32),
+                "triclinic": np.array([50, 50, 50, 70.53571, 109.48542, 70.518196], dtype=np.float32)}
+        res = np.empty((n, n), dtype=np.float64)
+        have_ref = orc.have_reference()
+        for name, b6 in box6.items():
+            gd.distance_array(x0, x1, box=b6, result=res)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                gd.distance_array(x0, x1, box=b6, result=res)
+            t_gpu = (time.perf_counter() - t0) / 3
+            entry = {"pairs": n * n, "gpu_call_ms": t_gpu * 1e3,
+                     "note": "distance_array(ndarray, ndarray, box, result=ndarray): H2D + kernel + D2H of the 89 MB result"}
+            if have_ref:
+                t0 = time.perf_counter()
+                want = orc.distance_array(x0, x1, b6, impl="reference")
+                entry["cpu_serial_ms"] = (time.perf_counter() - t0) * 1e3
+                if orc.have_reference(openmp=True):
+                    t0 = time.perf_counter()
+                    orc.distance_array(x0, x1, b6, impl="reference", openmp=True)
+                    entry["cpu_openmp_ms"] = (time.perf_counter() - t0) * 1e3
+                    entry["cpu_cores"] = len(os.sched_getaffinity(0))
+                entry["identical"] = bool(np.array_equal(res, want))
+            out[f"c1_single_call_{name}"] = entry
+    except Exception as e:                                            # the baseline is optional here
+        out["c1_single_call_error"] = repr(e)
     del outbuf, sout, ref, conf, xyz
     torch.cuda.empty_cache()
 
