@@ -404,9 +404,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dist_ready = world > 1
     if dist_ready:
-        # stdout carries ONE JSON line: keep NCCL's version banner out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries ONE JSON line: NCCL's banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from mdanalysis_b200 import FrameBlock, _cabi
     from mdanalysis_b200.analysis.rdf import InterRDF
