@@ -162,3 +162,38 @@ def test_batched_frames_c_abi(oracle):
     for f in range(F):
         assert np.array_equal(out[f], oracle.distance_array(ref[f], conf[f], b6))
         assert np.array_equal(so[f], oracle.self_distance_array(ref[f], b6))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bname", ["none", "ortho"])
+def test_self_distance_array_100k_atoms_materialised(oracle, bname):
+    """Config C5 at full size: 100 000 atoms -> 4 999 950 000 distances (40 GB, one buffer on the
+    device).  Checked through 200 000 sampled entries against the oracle's pair arithmetic (the
+    packed index k = i(2n-i-1)/2 + (j-i-1), calc_distances.h:457-458, is part of what is tested)."""
+    import torch
+    from mdanalysis_b200 import _cabi
+    n = 100_000
+    free, _ = torch.cuda.mem_get_info()
+    if free < 48 * 2 ** 30:
+        pytest.skip("needs 40 GB of free device memory")
+    rng = np.random.default_rng(55)
+    L = 215.44
+    x = (rng.random((n, 3)) * L * 1.05).astype(np.float32)
+    box = None if bname == "none" else np.array([L, L, L, 90, 90, 90], dtype=np.float32)
+    xd = torch.as_tensor(x[None]).cuda()
+    out = torch.empty(n * (n - 1) // 2, dtype=torch.float64, device="cuda")
+    mode = 0 if box is None else 1
+    b3 = None if box is None else np.ascontiguousarray(box[:3])
+    _cabi.check(_cabi.load().mdagpu_self_distance_array(_cabi.tensor_ptr(xd), n, mode, _cabi.ptr(b3),
+                                                        _cabi.tensor_ptr(out), 1, 1, _cabi.current_stream(xd)))
+    i = rng.integers(0, n - 1, 200_000)
+    j = i + 1 + (rng.integers(0, n, 200_000) % (n - 1 - i))
+    k = i * (2 * n - i - 1) // 2 + (j - i - 1)
+    got = out[torch.as_tensor(k, device="cuda")].cpu().numpy()
+    want = oracle.calc_bonds(np.ascontiguousarray(x[j]), np.ascontiguousarray(x[i]), box)
+    assert np.array_equal(got, want)
+    # first and last entries of the packed triangle
+    ends = out[[0, -1]].cpu().numpy()
+    assert np.array_equal(ends, oracle.calc_bonds(x[[1, n - 1]], x[[0, n - 2]], box))
+    del out
+    torch.cuda.empty_cache()

@@ -152,3 +152,60 @@ def test_contact_matrix(oracle):
         want = np.zeros((500, 500), dtype=bool)
         want[pairs[:, 0], pairs[:, 1]] = True
         assert np.array_equal(adj, want) and adj.diagonal().all()
+
+
+def _fastns_distance(oracle, a, b, box):
+    """Distance of FastNS.calc_distsq (nsgrid.pyx:483-497) for pairs of atoms: both wrapped into the
+    cell first, float32 difference, then the lazy orthorhombic image or the 27-image search."""
+    if np.all(box[3:] == 90.0):
+        aw, bw = oracle.apply_PBC(a, box), oracle.apply_PBC(b, box)
+        d = (aw - bw).astype(np.float64)
+        Lh = box[:3].astype(np.float64)
+        half = (0.5 * box[:3].astype(np.float64)).astype(np.float32).astype(np.float64)
+        d = np.where(d > half, d - Lh, np.where(d <= -half, d + Lh, d))
+        return np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+    return oracle.calc_bonds(a, b, box)                    # wraps, then minimum_image_triclinic
+
+
+@pytest.mark.parametrize("angles", [(60, 60, 90), (90, 90, 90)])
+def test_fastns_one_million_atoms(oracle, angles):
+    """Config C3 at full size: 1 M atoms, 8 A, triclinic [L, L, L, 60, 60, 90] (and its
+    orthorhombic twin), ~107 M pairs.  Size-independent properties instead of a full oracle run:
+    (1) every unordered pair is reported once;
+    (2) a sample of 100 000 reported pairs carries exactly the reference's distance, <= cutoff;
+    (3) completeness: for 16 random atoms the oracle's search against ALL atoms finds exactly the
+        neighbours the GPU result lists for them;
+    (4) search(first 100 000 atoms) returns the ordered pairs of those atoms plus their self pairs."""
+    import torch
+    from mdanalysis_b200.lib.nsgrid import FastNS
+    nn, cutoff = 1_000_000, 8.0
+    vol_factor = 0.70710678 if angles[0] == 60 else 1.0
+    L = (nn / 0.1 / vol_factor) ** (1.0 / 3.0)
+    box = np.array([L, L, L, *angles], dtype=np.float32)
+    rng = np.random.default_rng(2026)
+    tv = oracle.triclinic_vectors(box).astype(np.float64)
+    xyz = (rng.random((nn, 3)) @ tv).astype(np.float32)
+    grid = FastNS(cutoff, torch.as_tensor(xyz).cuda(), box)
+    res = grid.self_search()
+    pairs, dist = res.get_pairs(), res.get_pair_distances()
+    del res
+    npairs = len(pairs)
+    assert 1.06e8 < npairs < 1.09e8                       # n * rho * 4/3 pi r^3 / 2 = 1.072e8
+    lo, hi = np.minimum(pairs[:, 0], pairs[:, 1]), np.maximum(pairs[:, 0], pairs[:, 1])
+    assert (lo < hi).all()
+    skey = np.sort(lo.astype(np.int64) * nn + hi)
+    assert (np.diff(skey) > 0).all()                                              # (1)
+    s = rng.integers(0, npairs, 100_000)
+    want = _fastns_distance(oracle, np.ascontiguousarray(xyz[pairs[s, 0]]), np.ascontiguousarray(xyz[pairs[s, 1]]), box)
+    assert np.array_equal(dist[s], want) and (dist[s] <= cutoff).all()           # (2)
+    probe = rng.integers(0, nn, 16)
+    op, _ = oracle.capped_distance(np.ascontiguousarray(xyz[probe]), xyz, cutoff, box=box, method="nsgrid")
+    for t, atom in enumerate(probe):                                              # (3)
+        nb = op[op[:, 0] == t][:, 1]
+        nb = nb[nb != atom]
+        k = np.minimum(nb, atom).astype(np.int64) * nn + np.maximum(nb, atom)
+        pos = np.searchsorted(skey, k)
+        assert (pos < npairs).all() and np.array_equal(skey[pos], k)
+        assert int((lo == atom).sum() + (hi == atom).sum()) == len(nb)
+    n_search = len(grid.search(torch.as_tensor(xyz[:100_000]).cuda()))
+    assert n_search == int((lo < 100_000).sum() + (hi < 100_000).sum()) + 100_000    # (4)
