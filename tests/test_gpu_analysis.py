@@ -358,3 +358,76 @@ def test_interrdf_quad_kernel_against_row_kernel(oracle, case, monkeypatch):
     # host-resident frames go through the upload ring in pieces
     got_h = InterRDF(FrameBlock(pos, box), None, **kw).run().results.count
     assert np.array_equal(got_h, want)
+
+
+@pytest.mark.gpu
+def test_rmsd_aligntraj_full_size_c4(oracle):
+    """Config C4 at full size: 50 000 frames of a 10 000-atom structure (6 GB, generated on the
+    device): RMSD (plain and mass-weighted) and AlignTraj over all frames in one call each; 40
+    sampled frames are checked against the oracle (float64 QCP: rtol 1e-9 observed ~1e-13;
+    aligned coordinates within 1 ulp-ish of float32, 8e-6 A at these magnitudes)."""
+    import torch
+    from mdanalysis_b200.lib import qcprot
+    F, N = 50_000, 10_000
+    free, _ = torch.cuda.mem_get_info()
+    if free < 16 * 2 ** 30:
+        pytest.skip("needs 16 GB of free device memory")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(2026_4)
+    ref = torch.randn((N, 3), generator=g, device="cuda") * 20.0
+    quat = torch.randn((F, 4), generator=g, device="cuda")
+    quat = quat / quat.norm(dim=1, keepdim=True)
+    w, x, y, z = quat.unbind(1)
+    Q = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                     2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                     2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=1).reshape(F, 3, 3)
+    trans = torch.randn((F, 1, 3), generator=g, device="cuda") * 5.0
+    traj = torch.empty((F, N, 3), dtype=torch.float32, device="cuda")
+    for f0 in range(0, F, 5000):                          # chunks: bounded temporaries
+        sl = slice(f0, f0 + 5000)
+        traj[sl] = torch.matmul(ref[None], Q[sl]) + trans[sl] + torch.randn((5000, N, 3), generator=g, device="cuda")
+    refh = ref.cpu().numpy().astype(np.float32)
+    masses = np.random.default_rng(4).uniform(1, 32, N)
+    pick = np.sort(np.random.default_rng(5).choice(F, 40, replace=False))
+    sample = traj[torch.as_tensor(pick, device="cuda")].cpu().numpy()
+    for wts in (None, masses):
+        wn = None if wts is None else wts / wts.mean()
+        vals, _, _ = qcprot.qcp_trajectory(traj, refh, weights=wn, convention=0)
+        vals = vals.cpu().numpy()
+        assert vals.shape == (F,) and np.isfinite(vals).all() and 1.5 < vals.mean() < 2.0   # noise sigma 1 per axis
+        want = oracle.rmsd_trajectory(sample, refh, weights=wts)
+        assert np.allclose(vals[pick], want, rtol=1e-9, atol=0)
+    vals, _, moved = qcprot.qcp_trajectory(traj, refh, align=True, convention=1, out=traj)
+    assert moved is traj
+    aligned_want, rm_want = oracle.align_trajectory(sample, refh)
+    assert np.allclose(vals.cpu().numpy()[pick], rm_want, rtol=1e-9, atol=0)
+    got = traj[torch.as_tensor(pick, device="cuda")].cpu().numpy()
+    assert np.abs(got - aligned_want).max() <= 8e-6
+    # after the superposition every frame sits on the reference up to the noise
+    dev = (traj[::997] - ref[None]).pow(2).sum(-1).mean(-1).sqrt()
+    assert float(dev.max()) < 2.0
+
+
+@pytest.mark.gpu
+def test_interrdf_full_size_c2(oracle):
+    """Config C2 at full size (33 334 sites, 1000 frames, 150 bins to 15 A): additivity over frame
+    blocks (counts of the whole run == sum of the counts of its halves, through different chunking
+    and the host upload ring), the self-pair count, and the first two frames against the oracle."""
+    import torch
+    from mdanalysis_b200 import FrameBlock
+    from mdanalysis_b200.analysis.rdf import InterRDF
+    F, N, L = 1000, 33334, 100.0
+    box = np.array([L, L, L, 90, 90, 90], dtype=np.float32)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(20261018)
+    pos = (torch.rand((F, N, 3), generator=g, device="cuda") * L).contiguous()
+    blk = FrameBlock(pos, box)
+    whole = InterRDF(blk, None, nbins=150, range=(0.0, 15.0)).run().results
+    a = InterRDF(blk, None, nbins=150, range=(0.0, 15.0)).run(stop=431).results.count
+    b = InterRDF(FrameBlock(pos[431:].cpu().numpy(), box), None, nbins=150, range=(0.0, 15.0)).run().results.count
+    assert np.array_equal(whole.count, a + b)
+    assert whole.count[0] >= F * N and whole.count.sum() > 1.5e10      # 15.7 M ordered pairs per frame
+    assert abs(whole.rdf[100:].mean() - 1.0) < 2e-3                    # ideal gas: g(r) = 1
+    two = InterRDF(blk, None, nbins=150, range=(0.0, 15.0)).run(stop=2).results.count
+    h = pos[:2].cpu().numpy()
+    assert np.array_equal(two, oracle.interrdf(h, h, box, nbins=150, rrange=(0.0, 15.0))["count"])
