@@ -235,3 +235,36 @@ def test_cuda_backend_executor_for_analysisbase_run(mda):
     u = _universe(mda, traj, np.tile(np.array([80, 80, 80, 90, 90, 90], dtype=np.float32), (F, 1)), masses)
     with pytest.raises(ValueError):                  # the reference itself refuses: not parallelizable
         InterRDF(u.atoms, u.atoms).run(backend=cuda_backend(), unsupported_backend=True)
+
+
+def test_config_c1_adk_all_frames(mda):
+    """Config C1 as BASELINE.json states it: distance_array + self_distance_array on the
+    MDAnalysisTests adk PSF/DCD (3341 atoms, 98 frames), read by the reference itself; every frame,
+    no box / orthorhombic / triclinic, backend='cuda' against the reference's OpenMP build
+    (bit-identical to its serial build; used here only because it is 10x faster on the host)."""
+    import MDAnalysis.lib.distances as D
+    psf = os.path.join(REF, "MDAnalysisTests", "data", "adk.psf")
+    dcd = os.path.join(REF, "MDAnalysisTests", "data", "adk_dims.dcd")
+    if not (os.path.exists(psf) and os.path.exists(dcd)):
+        pytest.skip("adk PSF/DCD not present in baseline/_ref")
+    u = mda.Universe(psf, dcd)
+    assert u.atoms.n_atoms == 3341 and len(u.trajectory) == 98
+    boxes = [None, np.array([50, 50, 50, 90, 90, 90], dtype=np.float32),
+             np.array([50, 50, 50, 70.53571, 109.48542, 70.518196], dtype=np.float32)]
+    u.trajectory[0]
+    x0 = u.atoms.positions.copy()
+    cpu = "openmp" if "openmp" in D._distances else "serial"
+    for ts in u.trajectory:
+        x = u.atoms.positions
+        for box in boxes:
+            d = D.distance_array(x0, x, box=box, backend="cuda")
+            assert np.array_equal(d, D.distance_array(x0, x, box=box, backend=cpu))
+            if ts.frame % 14 == 0:
+                assert np.array_equal(D.self_distance_array(x, box=box, backend="cuda"),
+                                      D.self_distance_array(x, box=box, backend=cpu))
+    # the constants the reference's own test pins (lib/test_distances.py:439-454): frame 0 vs frame 10,
+    # to the 5 decimals that test asks for
+    u.trajectory[10]
+    d = D.distance_array(x0, u.atoms.positions, backend="cuda")
+    assert d.min() == pytest.approx(0.11981228170520701, abs=1e-5)
+    assert d.max() == pytest.approx(53.572192429459619, abs=1e-5)
