@@ -6,11 +6,13 @@
 // from the original coordinates.  Reference: package/MDAnalysis/analysis/rdf.py:268-291
 // (capped_distance + np.histogram) and lib/nsgrid.pyx:483-644.  What is different:
 //
-//  * WARPS ARE INDEPENDENT.  Each warp stages the candidates ITS queries need (the union of
-//    its lanes' cell windows in the stencil row) into a private two-buffer ring with 4-byte
-//    cp.async copies, one row ahead of the arithmetic; __syncwarp is the only
-//    synchronisation in the main loop.  (With CTA-wide stages 27 % of the warp samples sat
-//    at the barrier, profiles/r01e_*.)
+//  * ALL stencil rows of the CTA are staged ONCE (13 rows for a self RDF with the 5x5x5
+//    stencil: 15-41 kB), by 4-byte cp.async copies issued by all threads; after one
+//    __syncthreads every lane walks its windows in all rows with no further synchronisation.
+//    (Row-by-row stages cost a barrier each: 27 % of the warp samples sat there.  Rows that
+//    do not fit the tile -- dense systems -- are staged in groups of rows / pieces of a row.)
+//    A 224-thread CTA takes a whole row of home cells when its queries fit, 128-thread CTAs
+//    take runs of R cells otherwise (rdf.cu).
 //  * The copies TRANSPOSE: x[], y[], z[] planes, every run of the row (x-wrap left / in
 //    range / x-wrap right) padded to a multiple of four with far-away sentinels.  One
 //    LDS.128 per plane feeds four candidates, and two candidates share every arithmetic
