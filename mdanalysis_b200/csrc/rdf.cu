@@ -529,17 +529,33 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
         MDA_CUDA(pipe.init(A, same ? nullptr : B, na, nb, chunk, st));
     }
 
+    // piece schedule: device input in equal chunks; host input starts small (the first upload is
+    // the only one nothing hides) and doubles up to the ring's buffer size
+    std::vector<uint64_t> piece_start;
+    {
+        uint64_t size = chunk;
+        if (space == MDAGPU_HOST) {
+            size = chunk / 8;
+            if (size < 16) size = 16;
+            if (size > chunk) size = chunk;
+        }
+        for (uint64_t f0 = 0; f0 < nframes;) {
+            piece_start.push_back(f0);
+            f0 += size;
+            size = size * 2 > chunk ? chunk : size * 2;
+        }
+        piece_start.push_back(nframes);
+    }
+
     DevBuf fg_dev;
-    uint64_t piece_no = 0;
-    for (uint64_t f0 = 0; f0 < nframes; f0 += chunk, ++piece_no) {
-        const uint64_t fc = (nframes - f0 < chunk) ? nframes - f0 : chunk;
+    for (uint64_t piece_no = 0; piece_no + 1 < piece_start.size(); ++piece_no) {
+        const uint64_t f0 = piece_start[piece_no], fc = piece_start[piece_no + 1] - f0;
         const float *a_dev = A + f0 * na * 3, *b_dev = same ? nullptr : B + f0 * nb * 3;
         if (space == MDAGPU_HOST) {
             if (piece_no == 0) MDA_CUDA(pipe.upload(0, f0, fc));
-            if (f0 + chunk < nframes) {
-                const uint64_t f1 = f0 + chunk, fn = (nframes - f1 < chunk) ? nframes - f1 : chunk;
-                MDA_CUDA(pipe.upload(piece_no + 1, f1, fn));
-            }
+            if (piece_no + 2 < piece_start.size())
+                MDA_CUDA(pipe.upload(piece_no + 1, piece_start[piece_no + 1],
+                                     piece_start[piece_no + 2] - piece_start[piece_no + 1]));
             MDA_CUDA(pipe.acquire(piece_no, &a_dev, &b_dev));
         }
         uint64_t total_cells;
