@@ -234,6 +234,16 @@ MDAGPU_API int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
                           double r_hi, int excl_a, int excl_b, unsigned long long *counts,
                           int space, mdagpu_stream_t stream);
 
+/* InterRDF(exclude_same=...)  analysis/rdf.py:280-285: as mdagpu_rdf_accumulate, but a pair (i, j) is
+ * dropped when ids_a[i] == ids_b[j] (host int32 [na], [nb]: residue / segment / chain index of each
+ * atom; ids_b may be NULL for the same group). */
+MDAGPU_API int mdagpu_rdf_accumulate_ids(const float *A, uint64_t na, const float *B, uint64_t nb,
+                              uint64_t nframes, const float *box6, const float *h9,
+                              int boxes_per_frame, int mic, int wrap, double cutoff, double d2_max,
+                              int use_grid, const double *thresholds, int nbins, double r_lo,
+                              double r_hi, const int32_t *ids_a, const int32_t *ids_b,
+                              unsigned long long *counts, int space, mdagpu_stream_t stream);
+
 /* InterRDF_s  analysis/rdf.py:585-597: as mdagpu_rdf_accumulate, but one histogram per
  * (site i of A, site j of B): counts is uint64 [na, nb, nbins] (nb = na when B is NULL /
  * the same array), accumulated into. */

@@ -55,6 +55,8 @@ SIGNATURES = {
     "mdagpu_qcp_trajectory": (_i, [_vp, _u64, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mdagpu_rdf_accumulate": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,
                                    _d, _d, _i, _i, _vp, _i, _vp]),
+    "mdagpu_rdf_accumulate_ids": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,
+                                       _d, _d, _vp, _vp, _vp, _i, _vp]),
     "mdagpu_rdf_sites_accumulate": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,
                                          _d, _d, _vp, _i, _vp]),
     "mdagpu_contacts_self": (_i, [_vp, _u64, _u64, _i, _vp, _d, _d, _vp, _vp, _i, _vp]),

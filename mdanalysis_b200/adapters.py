@@ -51,8 +51,9 @@ def _finish(analysis, gpu):
 
 def _run_interrdf(an, idx, device):
     from .analysis.rdf import InterRDF
-    if getattr(an, "exclude_same", None) is not None:
-        raise NotImplementedError("exclude_same needs topology ids; use exclusion_block on the GPU path")
+    ids = None
+    if getattr(an, "exclude_same", None) is not None:       # the attribute name: resindices / segindices / chainIDs
+        ids = (np.asarray(getattr(an.g1, an.exclude_same)), np.asarray(getattr(an.g2, an.exclude_same)))
     b1 = _block(an.g1, idx)
     same = an.g2 is an.g1 or (len(an.g1) == len(an.g2) and np.array_equal(an.g1.indices, an.g2.indices))
     b2 = b1 if same else _block(an.g2, idx)
@@ -60,7 +61,7 @@ def _run_interrdf(an, idx, device):
         b1 = b1.to_device()
         b2 = b1 if same else b2.to_device()
     gpu = InterRDF(b1, b2, nbins=an.rdf_settings["bins"], range=an.rdf_settings["range"], norm=an.norm,
-                   exclusion_block=an._exclusion_block).run()
+                   exclusion_block=an._exclusion_block, exclude_same=ids).run()
     for k in ("count", "edges", "bins", "rdf"):
         an.results[k] = gpu.results[k]
     an.volume_cum = gpu.volume_cum

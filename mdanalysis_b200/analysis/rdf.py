@@ -68,6 +68,7 @@ class InterRDF(BlockAnalysis):
 
     def __init__(self, g1, g2, nbins=75, range=(0.0, 15.0), norm="rdf", exclusion_block=None,
                  exclude_same=None, dimensions=None, distributed=False, **kwargs):
+        ids = self._resolve_exclude_same(g1, g2, exclude_same, exclusion_block)
         b1 = as_block(g1, dimensions)
         # distributed=True: this rank holds one shard of the frames; counts, volume
         # and frame count are summed over ranks (NCCL all_reduce on the device
@@ -81,17 +82,39 @@ class InterRDF(BlockAnalysis):
         self.norm = str(norm).lower()
         self.rdf_settings = {"bins": nbins, "range": range}
         self._exclusion_block = exclusion_block
-        if exclude_same is not None:
+        self._exclude_ids = ids
+        if ids is not None and (len(ids[0]) != b1.n_atoms or len(ids[1]) != self._b2.n_atoms):
+            raise ValueError("exclude_same ids must have one entry per atom of g1 and of g2")
+        if self.norm not in ["rdf", "density", "none"]:
+            raise ValueError(f"'{self.norm}' is an invalid norm. Use 'rdf', 'density' or 'none'.")
+
+    @staticmethod
+    def _resolve_exclude_same(g1, g2, exclude_same, exclusion_block):
+        """exclude_same -> (ids of g1's atoms, ids of g2's atoms) as int32, or None.
+
+        The reference takes 'residue' | 'segment' | 'chain' and reads ``resindices`` /
+        ``segindices`` / ``chainIDs`` from the AtomGroups (rdf.py:245-247, 280-285); with bare
+        arrays or FrameBlocks pass the two id arrays themselves: ``exclude_same=(ids1, ids2)``."""
+        if exclude_same is None:
+            return None
+        if isinstance(exclude_same, str):
             if exclude_same not in ["residue", "segment", "chain"]:
                 raise ValueError("The exclude_same argument to InterRDF must be None, 'residue', "
                                  "'segment' or 'chain'.")
-            if exclusion_block is not None:
-                raise ValueError("The exclude_same argument to InterRDF cannot be used with "
-                                 "exclusion_block.")
-            raise NotImplementedError("exclude_same is not available in the cuda backend yet; "
-                                      "use exclusion_block")
-        if self.norm not in ["rdf", "density", "none"]:
-            raise ValueError(f"'{self.norm}' is an invalid norm. Use 'rdf', 'density' or 'none'.")
+            attr = {"residue": "resindices", "segment": "segindices", "chain": "chainIDs"}[exclude_same]
+            g2 = g1 if g2 is None else g2
+            if not (hasattr(g1, attr) and hasattr(g2, attr)):
+                raise TypeError(f"exclude_same='{exclude_same}' needs AtomGroups with .{attr}; with arrays pass "
+                                "exclude_same=(ids_of_g1_atoms, ids_of_g2_atoms)")
+            a, b = np.asarray(getattr(g1, attr)), np.asarray(getattr(g2, attr))
+        else:
+            a, b = (np.asarray(x) for x in exclude_same)
+        if exclusion_block is not None:
+            raise ValueError("The exclude_same argument to InterRDF cannot be used with "
+                             "exclusion_block.")
+        _, inv = np.unique(np.concatenate([a, b]), return_inverse=True)     # any dtype (chain ids are strings)
+        inv = inv.astype(np.int32)
+        return np.ascontiguousarray(inv[:len(a)]), np.ascontiguousarray(inv[len(a):])
 
     def run(self, start=None, stop=None, step=None, frames=None, **kwargs):
         idx = self._slice(start, stop, step, frames)
@@ -158,6 +181,21 @@ class InterRDF(BlockAnalysis):
             box6 = np.ascontiguousarray(dims[:1] if const else dims, dtype=np.float32)
             h9 = np.ascontiguousarray([triclinic_vectors(b).reshape(9) for b in box6], dtype=np.float32)
             d2_max = rc2 if use_grid else d2_brute
+            if self._exclude_ids is not None:
+                ida, idb = self._exclude_ids
+                if dev:
+                    A = A.contiguous()
+                    Bp = None if B is None else tensor_ptr(B.contiguous())
+                    Ap, cp, sp_, strm = tensor_ptr(A), tensor_ptr(counts), DEVICE, current_stream(A)
+                else:
+                    A = np.ascontiguousarray(A)
+                    B = None if B is None else np.ascontiguousarray(B)
+                    Ap, Bp, cp, sp_, strm = ptr(A), ptr(B), ptr(counts), HOST, None
+                check(load().mdagpu_rdf_accumulate_ids(
+                    Ap, na, Bp, nb, len(fidx), ptr(box6), ptr(h9), int(not const), mic, wrap,
+                    float(self._maxrange), d2_max, use_grid, ptr(thr), nbins, lo, hi, ptr(ida), ptr(idb),
+                    cp, sp_, strm))
+                continue
             if dev:
                 A = A.contiguous()
                 Bp = None if B is None else tensor_ptr(B.contiguous())

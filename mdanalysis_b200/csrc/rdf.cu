@@ -63,6 +63,7 @@ struct HistSink {
     int nbins, excl_a, excl_b;
     float c0, inv_dr, band_lim, d2_fast_max;     // c0 = -lo*inv_dr - 0.5, band_lim = 0.5 - band
     uint32_t hb;                  // shared address of this warp's histogram, biased (see begin())
+    const int *ids_a, *ids_b;     // exclude_same: per-atom group ids (device) or NULL
 
     __device__ __forceinline__ uint32_t *mine() const
     {
@@ -78,7 +79,9 @@ struct HistSink {
     }
     __device__ __forceinline__ bool excluded(int i, int j) const
     {
-        return EXCL && (i / excl_a) == (j / excl_b);   // rdf.py:274-278
+        if (!EXCL) return false;
+        if (ids_a) return ids_a[i] == ids_b[j];          // exclude_same, rdf.py:280-285
+        return (i / excl_a) == (j / excl_b);             // exclusion_block, rdf.py:274-278
     }
     // an unordered pair seen once stands for (i,j) and (j,i)
     template <bool SYM> __device__ __forceinline__ uint32_t weight_of(int i, int j) const
@@ -159,12 +162,14 @@ struct HistSinkGlobal {
     unsigned long long *counts;
     int nbins, excl_a, excl_b;
     float lo, inv_dr;
+    const int *ids_a, *ids_b;
     __device__ __forceinline__ bool try_fast(int, int, float) { return false; }
     template <bool SYM> __device__ __forceinline__ bool try_fast_w(int, int, float) { return false; }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void end() {}
     __device__ __forceinline__ bool excluded(int i, int j) const
     {
+        if (ids_a) return ids_a[i] == ids_b[j];
         return excl_a > 0 && (i / excl_a) == (j / excl_b);
     }
     template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t)
@@ -408,6 +413,7 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
                                int boxes_per_frame, int mic, int wrap, double cutoff,
                                double d2_max, int use_grid, const double *thresholds,
                                int nbins, double r_lo, double r_hi, int excl_a, int excl_b,
+                               const int32_t *ids_a_host, const int32_t *ids_b_host,
                                unsigned long long *counts, int per_site, int space, mdagpu_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
@@ -465,7 +471,8 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     const int64_t cells_per_frame = boxes_per_frame ? 0 : fgs[0].grid.ncell_total;
     // the packed kernel (rowquad.cuh) folds the cutoff into the top histogram edge, has no
     // exclusion blocks and keeps one 32-bit histogram per warp of a 128-thread CTA
-    const bool quad = !per_site && W > 0 && mic == MIC_ORTHO_LAZY && r_hi > 0.0 && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max
+    const bool by_ids = ids_a_host != nullptr;
+    const bool quad = !per_site && !by_ids && W > 0 && mic == MIC_ORTHO_LAZY && r_hi > 0.0 && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max
                       && excl_a == 0 && (size_t)nbins * 4 * sizeof(uint32_t) <= 160 * 1024
                       && !getenv("MDAGPU_RDF_NO_QUAD");
     double d_abs_err = 0.0;
@@ -476,8 +483,13 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
         d_abs_err = fmax(d_abs_err, e);
     }
 
-    StagedIn thr_in;
+    StagedIn thr_in, ida_in, idb_in;
     StagedOut cnt;
+    if (by_ids) {      // exclude_same: group ids of the atoms of A and of B (host arrays)
+        MDA_CUDA(ida_in.init(ids_a_host, na * sizeof(int32_t), MDAGPU_HOST, st));
+        MDA_CUDA(idb_in.init(ids_b_host ? ids_b_host : ids_a_host, nb * sizeof(int32_t), MDAGPU_HOST, st));
+    }
+    const int *ida = by_ids ? ida_in.as<int>() : nullptr, *idb = by_ids ? idb_in.as<int>() : nullptr;
     MDA_CUDA(thr_in.init(thresholds, (size_t)(nbins + 1) * sizeof(double), MDAGPU_HOST, st));   // always a host array
     const size_t n_hist = per_site ? (size_t)na * (size_t)nb : 1;          // histograms in `counts`
     MDA_CUDA(cnt.init(counts, n_hist * (size_t)nbins * sizeof(unsigned long long), space, st, true));
@@ -649,7 +661,7 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
 #define COMMA ,
 #define RUN_HIST(SINK)                                                                              \
     do {                                                                                           \
-        SINK sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, c0, inv_dr, band_lim, d2_fast_max, 0u }; \
+        SINK sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, c0, inv_dr, band_lim, d2_fast_max, 0u, ida, idb }; \
         rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, hist_bytes, st); \
     } while (0)
         if (per_site) {
@@ -657,10 +669,10 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, 0, st);
         }
         else if (!fits) {
-            HistSinkGlobal sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, (float)r_lo, inv_dr };
+            HistSinkGlobal sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, excl_a, excl_b, (float)r_lo, inv_dr, ida, idb };
             rc = dispatch_hist(mic, same, qq, cl, fgd, boxes_per_frame, fc, tv, spc, sink, 0, st);
         }
-        else if (excl_a > 0) {
+        else if (excl_a > 0 || by_ids) {
             if (threads == 192) RUN_HIST(HistSink<192 COMMA true>);
             else if (threads == 128) RUN_HIST(HistSink<128 COMMA true>);
             else RUN_HIST(HistSink<64 COMMA true>);
@@ -688,7 +700,22 @@ extern "C" int mdagpu_rdf_accumulate(const float *A, uint64_t na, const float *B
                                      unsigned long long *counts, int space, mdagpu_stream_t stream)
 {
     return rdf_accumulate_impl(A, na, B, nb, nframes, box6, h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
-                               use_grid, thresholds, nbins, r_lo, r_hi, excl_a, excl_b, counts, 0, space, stream);
+                               use_grid, thresholds, nbins, r_lo, r_hi, excl_a, excl_b, nullptr, nullptr, counts, 0,
+                               space, stream);
+}
+
+extern "C" int mdagpu_rdf_accumulate_ids(const float *A, uint64_t na, const float *B, uint64_t nb,
+                                         uint64_t nframes, const float *box6, const float *h9,
+                                         int boxes_per_frame, int mic, int wrap, double cutoff,
+                                         double d2_max, int use_grid, const double *thresholds,
+                                         int nbins, double r_lo, double r_hi, const int32_t *ids_a,
+                                         const int32_t *ids_b, unsigned long long *counts, int space,
+                                         mdagpu_stream_t stream)
+{
+    MDA_REQUIRE(ids_a != nullptr, "mdagpu_rdf_accumulate_ids: ids_a is NULL");
+    MDA_REQUIRE(ids_b != nullptr || B == nullptr || B == A, "mdagpu_rdf_accumulate_ids: ids_b is NULL");
+    return rdf_accumulate_impl(A, na, B, nb, nframes, box6, h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
+                               use_grid, thresholds, nbins, r_lo, r_hi, 0, 0, ids_a, ids_b, counts, 0, space, stream);
 }
 
 extern "C" int mdagpu_rdf_sites_accumulate(const float *A, uint64_t na, const float *B, uint64_t nb,
@@ -701,7 +728,7 @@ extern "C" int mdagpu_rdf_sites_accumulate(const float *A, uint64_t na, const fl
     MDA_REQUIRE(na * nb <= (1ull << 26), "mdagpu_rdf_sites_accumulate: %llu x %llu site pairs is too many "
                 "(one histogram each)", (unsigned long long)na, (unsigned long long)(B && B != A ? nb : na));
     return rdf_accumulate_impl(A, na, B, nb, nframes, box6, h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
-                               use_grid, thresholds, nbins, r_lo, r_hi, 0, 0, counts, 1, space, stream);
+                               use_grid, thresholds, nbins, r_lo, r_hi, 0, 0, nullptr, nullptr, counts, 1, space, stream);
 }
 
 extern "C" int mdagpu_contacts_self(const float *xyz, uint64_t n, uint64_t nframes, int box_mode,

@@ -658,7 +658,7 @@ def align_trajectory(traj, reference, select=None, weights=None):
 # InterRDF (analysis/rdf.py:253-316)
 # --------------------------------------------------------------------------
 def interrdf(pos_a, pos_b, dimensions, nbins=75, rrange=(0.0, 15.0), norm="rdf",
-             exclusion_block=None, frames=None):
+             exclusion_block=None, frames=None, exclude_same_ids=None):
     """pos_a [F,Na,3], pos_b [F,Nb,3] float32, dimensions [F,6] or [6]."""
     pos_a = np.asarray(pos_a, dtype=np.float32)
     pos_b = np.asarray(pos_b, dtype=np.float32)
@@ -676,6 +676,10 @@ def interrdf(pos_a, pos_b, dimensions, nbins=75, rrange=(0.0, 15.0), norm="rdf",
         if exclusion_block is not None:
             ia = pairs[:, 0] // exclusion_block[0]
             ib = pairs[:, 1] // exclusion_block[1]
+            dist = dist[np.where(ia != ib)[0]]
+        if exclude_same_ids is not None:                   # rdf.py:280-285
+            ia = np.asarray(exclude_same_ids[0])[pairs[:, 0]]
+            ib = np.asarray(exclude_same_ids[1])[pairs[:, 1]]
             dist = dist[np.where(ia != ib)[0]]
         c, _ = np.histogram(dist, bins=nbins, range=rrange)
         count += c

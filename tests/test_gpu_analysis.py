@@ -431,3 +431,40 @@ def test_interrdf_full_size_c2(oracle):
     two = InterRDF(blk, None, nbins=150, range=(0.0, 15.0)).run(stop=2).results.count
     h = pos[:2].cpu().numpy()
     assert np.array_equal(two, oracle.interrdf(h, h, box, nbins=150, rrange=(0.0, 15.0))["count"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bname", ["ortho", "tric60"])
+@pytest.mark.parametrize("same", [True, False])
+def test_interrdf_exclude_same(oracle, bname, same):
+    """exclude_same (rdf.py:280-285): pairs whose atoms carry the same residue / segment / chain
+    id are dropped; ids may be any dtype (chain ids are strings)."""
+    from mdanalysis_b200.analysis.rdf import InterRDF
+    from mdanalysis_b200 import FrameBlock
+    rng = np.random.default_rng(17)
+    box = BOXES[bname]
+    tv = oracle.triclinic_vectors(box).astype(np.float64)
+    F, N = 3, 1500
+    pos = np.stack([(rng.random((N, 3)) * 1.2 - 0.1) @ tv for _ in range(F)]).astype(np.float32)
+    resid = np.repeat(np.arange(N // 3), 3)
+    if same:
+        a = b = pos
+        g1 = g2 = FrameBlock(pos, box)
+        ids = (resid, resid)
+    else:
+        a, b = np.ascontiguousarray(pos[:, :900]), np.ascontiguousarray(pos[:, 600:])
+        g1, g2 = FrameBlock(a, box), FrameBlock(b, box)
+        ids = (np.array([f"c{r % 7}" for r in resid[:900]]), np.array([f"c{r % 7}" for r in resid[600:]]))
+    want = oracle.interrdf(a, b, box, nbins=60, rrange=(0.0, 6.0), exclude_same_ids=ids)
+    got = InterRDF(g1, g2, nbins=60, range=(0.0, 6.0), exclude_same=ids).run()
+    assert np.array_equal(got.results.count, want["count"])
+    assert np.allclose(got.results.rdf, want["rdf"], rtol=1e-12)
+    none = InterRDF(g1, g2, nbins=60, range=(0.0, 6.0)).run().results.count
+    assert got.results.count.sum() < none.sum()
+    got_d = InterRDF(g1.to_device(), g1.to_device() if same else g2.to_device(), nbins=60, range=(0.0, 6.0),
+                     exclude_same=ids).run()
+    assert np.array_equal(got_d.results.count, want["count"])
+    with pytest.raises(ValueError, match="cannot be used with"):
+        InterRDF(g1, g2, exclude_same=ids, exclusion_block=(3, 3))
+    with pytest.raises(TypeError, match="needs AtomGroups"):
+        InterRDF(g1, g2, exclude_same="residue")

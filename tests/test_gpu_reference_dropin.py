@@ -268,3 +268,23 @@ def test_config_c1_adk_all_frames(mda):
     d = D.distance_array(x0, u.atoms.positions, backend="cuda")
     assert d.min() == pytest.approx(0.11981228170520701, abs=1e-5)
     assert d.max() == pytest.approx(53.572192429459619, abs=1e-5)
+
+
+def test_interrdf_exclude_same_against_reference(mda):
+    """exclude_same='residue' on a universe with residues (three atoms each), reference vs
+    run_on_gpu (which reads the attribute the reference constructor resolved)."""
+    from MDAnalysis.analysis.rdf import InterRDF
+    from mdanalysis_b200 import run_on_gpu
+    rng = np.random.default_rng(91)
+    F, nres = 4, 500
+    N = 3 * nres
+    box = np.array([28, 30, 29, 90, 90, 90], dtype=np.float32)
+    pos = (rng.random((F, N, 3)) * box[:3]).astype(np.float32)
+    u = mda.Universe.empty(N, n_residues=nres, atom_resindex=np.repeat(np.arange(nres), 3), trajectory=True)
+    u.load_new(pos.copy(), order="fac", dimensions=np.tile(box, (F, 1)))
+    ow, hw = u.atoms[::3], u.atoms[np.arange(N) % 3 != 0]
+    for g1, g2 in ((ow, hw), (u.atoms, u.atoms)):
+        want = InterRDF(g1, g2, nbins=50, range=(0.0, 7.0), exclude_same="residue").run()
+        got = run_on_gpu(InterRDF(g1, g2, nbins=50, range=(0.0, 7.0), exclude_same="residue"))
+        assert np.array_equal(got.results.count, want.results.count)
+        assert np.allclose(got.results.rdf, want.results.rdf, rtol=1e-12)
