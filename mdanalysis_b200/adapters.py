@@ -16,7 +16,7 @@ What happens: the frames of the AtomGroups are read in bulk (``FrameBlock.from_a
 from the attributes the reference constructor left on the object, all frames go through the
 CUDA kernels in one call, and ``results`` / ``frames`` / ``times`` / ``n_frames`` are written
 back onto the reference object.  Supported: ``rdf.InterRDF``, ``rdf.InterRDF_s``, ``rms.RMSD``,
-``align.AlignTraj`` (in-memory trajectories), ``contacts.Contacts``.
+``align.AlignTraj`` and ``align.AverageStructure`` (in-memory trajectories), ``contacts.Contacts``.
 """
 from __future__ import annotations
 
@@ -128,6 +128,35 @@ def _run_aligntraj(an, idx, device):
     return _finish(an, gpu)
 
 
+def _run_average_structure(an, idx, device):
+    from .analysis.align import AverageStructure
+    if an.filename is not None:
+        raise NotImplementedError("AverageStructure on the GPU path needs in_memory=True")
+    mob_u, ref_u = an.mobile.universe, an.ref_atoms.universe
+    traj = mob_u.trajectory
+    arr, order = traj.get_array(), traj.stored_order
+    blk = _block(mob_u.atoms, idx)
+    cur = ref_u.trajectory.ts.frame
+    try:
+        ref_u.trajectory[an.ref_frame]
+        refblk = FrameBlock(ref_u.atoms.positions.copy()[None])
+    finally:
+        ref_u.trajectory[cur]
+    if device:
+        blk = blk.to_device()
+    w = an._weights
+    gpu = AverageStructure(blk, refblk, select={"mobile": an.mobile_atoms.indices, "reference": an.ref_atoms.indices},
+                           weights=None if w is None else np.asarray(w, dtype=np.float64), in_memory=True).run()
+    moved = blk.positions
+    moved = moved.detach().cpu().numpy() if hasattr(moved, "detach") else np.asarray(moved)
+    view = np.transpose(arr, [order.find(c) for c in "fac"])
+    view[idx] = moved
+    an.results.positions = gpu.results.positions
+    an.results.rmsd = gpu.results.rmsd
+    an.results.universe.load_new(an.results.positions.reshape((1, -1, 3)))      # align.py:1085-1087
+    return _finish(an, gpu)
+
+
 def _run_contacts(an, idx, device):
     from .analysis.contacts import pair_list_distances
     A, B = _block(an.grA, idx), _block(an.grB, idx)
@@ -151,7 +180,7 @@ def _run_contacts(an, idx, device):
 
 
 _RUNNERS = {"InterRDF": _run_interrdf, "InterRDF_s": _run_interrdf_s, "RMSD": _run_rmsd,
-            "AlignTraj": _run_aligntraj, "Contacts": _run_contacts}
+            "AlignTraj": _run_aligntraj, "AverageStructure": _run_average_structure, "Contacts": _run_contacts}
 
 
 def run_on_gpu(analysis, start=None, stop=None, step=None, frames=None, device=True):

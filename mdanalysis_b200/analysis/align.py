@@ -83,3 +83,66 @@ class AlignTraj(BlockAnalysis):
         self.results.positions = moved
         if self._in_memory:
             blk.positions = moved
+
+
+class AverageStructure(BlockAnalysis):
+    """Average structure after superposing every frame on a reference
+    (``analysis/align.py:870-1118``).
+
+    mobile     FrameBlock | [F, n, 3] array / CUDA tensor | AtomGroup; ALL atoms are moved
+               (``in_memory=True`` rewrites the block, as the reference rewrites its reader)
+    reference  block / positions of the reference (default: ``mobile``), frame ``ref_frame``
+    select     atoms that define the fit AND whose positions are averaged
+    After ``run()``: ``results.positions`` (float64 ``[n_sel, 3]``, the mean of the fitted
+    selected atoms over the frames) and ``results.rmsd`` (mean best-fit RMSD).  One
+    ``mdagpu_qcp_trajectory(align=1)`` launch superposes all frames; the mean is a float64
+    reduction over the aligned block.
+    """
+
+    def __init__(self, mobile, reference=None, select="all", weights=None, ref_frame=0, in_memory=True,
+                 **kwargs):
+        blk = as_block(mobile)
+        super().__init__(blk, **kwargs)
+        self._ref = blk if reference is None else as_block(reference)
+        self._sel_m = _resolve_selection(mobile, select["mobile"] if isinstance(select, dict) else select)
+        self._sel_r = _resolve_selection(reference if reference is not None else mobile,
+                                         select["reference"] if isinstance(select, dict) else select)
+        self._weights = weights
+        self._in_memory = in_memory
+        self.ref_frame = ref_frame
+        n_m = blk.n_atoms if self._sel_m is None else len(self._sel_m)
+        n_r = self._ref.n_atoms if self._sel_r is None else len(self._sel_r)
+        if n_m != n_r:
+            raise ValueError("Reference and trajectory atom selections do not contain the same "
+                             f"number of atoms: N_ref={n_r:d}, N_traj={n_m:d}")
+
+    def _prepare(self, blk):
+        ref = self._ref.positions[self.ref_frame]
+        if is_tensor(ref):
+            ref = ref.detach().cpu().numpy()
+        ref = np.array(ref, dtype=np.float32)                  # a copy: `mobile` may be rewritten below
+        self._ref_sel = ref if self._sel_r is None else ref[self._sel_r]
+
+    def _compute(self, blk):
+        w = None
+        if self._weights is not None:
+            if isinstance(self._weights, str):
+                w = get_weights(self._ref, self._weights)
+                w = w if self._sel_r is None else w[self._sel_r]
+            else:
+                w = np.asarray(self._weights, dtype=np.float64)
+            w = w / np.mean(w)
+        vals, _, moved = qcp.qcp_trajectory(
+            blk.positions, self._ref_sel, select=self._sel_m, weights=w, align=True, convention=1,
+            allclose_shortcut=(w is None), out=blk.positions if self._in_memory else None)
+        if self._in_memory:
+            blk.positions = moved
+        if is_tensor(moved):
+            import torch
+            sel = moved if self._sel_m is None else moved[:, torch.as_tensor(self._sel_m, device=moved.device)]
+            self.results.positions = sel.to(torch.float64).mean(dim=0).cpu().numpy()
+            self.results.rmsd = float(vals.to(torch.float64).mean())
+        else:
+            sel = moved if self._sel_m is None else moved[:, self._sel_m]
+            self.results.positions = sel.astype(np.float64).sum(axis=0) / blk.n_frames
+            self.results.rmsd = float(np.asarray(vals, dtype=np.float64).sum() / blk.n_frames)

@@ -288,3 +288,36 @@ def test_interrdf_exclude_same_against_reference(mda):
         got = run_on_gpu(InterRDF(g1, g2, nbins=50, range=(0.0, 7.0), exclude_same="residue"))
         assert np.array_equal(got.results.count, want.results.count)
         assert np.allclose(got.results.rdf, want.results.rdf, rtol=1e-12)
+
+
+def test_average_structure_against_reference(mda):
+    from MDAnalysis.analysis import align as ralign
+    from mdanalysis_b200 import FrameBlock, run_on_gpu
+    from mdanalysis_b200.analysis.align import AverageStructure
+    rng = np.random.default_rng(12)
+    F, N = 15, 700
+    ref_xyz = rng.normal(0, 9, (N, 3))
+    traj = np.stack([(ref_xyz @ np.linalg.qr(rng.normal(size=(3, 3)))[0] + rng.normal(0, 3, 3)
+                      + rng.normal(0, 0.5, (N, 3))) for _ in range(F)]).astype(np.float32)
+    masses = rng.uniform(1, 32, N)
+
+    def full(xyz):          # AverageStructure merges the selection into a new universe: needs a full topology
+        u = mda.Universe.empty(N, n_residues=N, atom_resindex=np.arange(N), n_segments=1,
+                               residue_segindex=np.zeros(N, dtype=int), trajectory=True)
+        u.add_TopologyAttr("masses", masses)
+        for attr, val in (("names", ["CA"] * N), ("types", ["C"] * N), ("resnames", ["ALA"] * N),
+                          ("resids", np.arange(1, N + 1)), ("segids", ["A"])):
+            u.add_TopologyAttr(attr, val)
+        u.load_new(xyz.copy(), order="fac")
+        return u
+    r = full(ref_xyz.astype(np.float32)[None])
+    for sel, w in (("all", None), ("index 0:399", "mass")):
+        want = ralign.AverageStructure(full(traj), r, select=sel, weights=w).run()
+        got = run_on_gpu(ralign.AverageStructure(full(traj), r, select=sel, weights=w))
+        assert np.allclose(got.results.positions, want.results.positions, rtol=0, atol=2e-5)
+        assert got.results.rmsd == pytest.approx(want.results.rmsd, rel=1e-9)
+        assert np.allclose(got.results.universe.atoms.positions, want.results.universe.atoms.positions, atol=2e-5)
+    idx = np.arange(400)
+    g = AverageStructure(FrameBlock(traj.copy(), masses=masses), FrameBlock(ref_xyz.astype(np.float32)[None], masses=masses),
+                         select=idx, weights="mass").run()
+    assert np.allclose(g.results.positions, want.results.positions, rtol=0, atol=2e-5)
