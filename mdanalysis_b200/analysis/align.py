@@ -132,17 +132,17 @@ class AverageStructure(BlockAnalysis):
             else:
                 w = np.asarray(self._weights, dtype=np.float64)
             w = w / np.mean(w)
+        import torch
+        host_input = not blk.on_device
+        pos = torch.as_tensor(blk.positions).cuda() if host_input else blk.positions     # reduce on the device
         vals, _, moved = qcp.qcp_trajectory(
-            blk.positions, self._ref_sel, select=self._sel_m, weights=w, align=True, convention=1,
-            allclose_shortcut=(w is None), out=blk.positions if self._in_memory else None)
+            pos, self._ref_sel, select=self._sel_m, weights=w, align=True, convention=1,
+            allclose_shortcut=(w is None), out=pos if (self._in_memory or host_input) else None)
         if self._in_memory:
-            blk.positions = moved
-        if is_tensor(moved):
-            import torch
-            sel = moved if self._sel_m is None else moved[:, torch.as_tensor(self._sel_m, device=moved.device)]
-            self.results.positions = sel.to(torch.float64).mean(dim=0).cpu().numpy()
-            self.results.rmsd = float(vals.to(torch.float64).mean())
-        else:
-            sel = moved if self._sel_m is None else moved[:, self._sel_m]
-            self.results.positions = sel.astype(np.float64).sum(axis=0) / blk.n_frames
-            self.results.rmsd = float(np.asarray(vals, dtype=np.float64).sum() / blk.n_frames)
+            if host_input:
+                blk.positions[...] = moved.cpu().numpy()
+            else:
+                blk.positions = moved
+        sel = moved if self._sel_m is None else moved[:, torch.as_tensor(self._sel_m, device=moved.device)]
+        self.results.positions = sel.to(torch.float64).mean(dim=0).cpu().numpy()
+        self.results.rmsd = float(vals.to(torch.float64).mean())

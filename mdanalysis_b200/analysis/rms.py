@@ -158,11 +158,13 @@ class RMSD(BlockAnalysis):
                                             weights=w, convention=0)
             out[:, 2] = vals.detach().cpu().numpy() if is_tensor(vals) else vals
             return
-        # secondary groups: superpose whole frames (rms.py:697-721), then plain RMSDs
-        vals, _, moved = qcp.qcp_trajectory(blk.positions, self._ref_sel, select=self._sel_m,
+        # secondary groups: superpose whole frames (rms.py:697-721), then plain RMSDs of the groups,
+        # reduced on the device in float64
+        import torch
+        pos = blk.positions if blk.on_device else torch.as_tensor(blk.positions).cuda()
+        vals, _, moved = qcp.qcp_trajectory(pos, self._ref_sel, select=self._sel_m,
                                             weights=w, align=True, convention=0)
-        out[:, 2] = vals.detach().cpu().numpy() if is_tensor(vals) else vals
-        moved = moved.detach().cpu().numpy() if is_tensor(moved) else moved
+        out[:, 2] = vals.detach().cpu().numpy()
         wg = self.weights_groupselections
         if not wg:
             wg = [self.weights if not np.iterable(self.weights) or isinstance(self.weights, str)
@@ -171,10 +173,10 @@ class RMSD(BlockAnalysis):
             gw = wg[k]
             if isinstance(gw, str) and gw == "mass":
                 gw = blk.masses[gm]
-            refpos = self._ref_all[gr].astype(np.float64)
+            refpos = torch.as_tensor(self._ref_all[gr].astype(np.float64), device=moved.device)
+            sel = moved[:, torch.as_tensor(np.asarray(gm), device=moved.device)].to(torch.float64)
+            diff2 = (sel - refpos[None]) ** 2
             if gw is not None:
                 gw = np.asarray(gw, dtype=np.float64) / np.mean(gw)
-            diff2 = (moved[:, gm].astype(np.float64) - refpos[None]) ** 2
-            if gw is not None:
-                diff2 = diff2 * gw[None, :, None]
-            out[:, 3 + k] = np.sqrt(diff2.sum(axis=(1, 2)) / len(gm))
+                diff2 = diff2 * torch.as_tensor(gw, device=moved.device)[None, :, None]
+            out[:, 3 + k] = torch.sqrt(diff2.sum(dim=(1, 2)) / len(gm)).cpu().numpy()
