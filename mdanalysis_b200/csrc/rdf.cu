@@ -535,7 +535,7 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     // HOST arrays; 400 MB per 1000 frames of C2 would otherwise sit in front of the kernels).
     HostPipe pipe;
     if (space == MDAGPU_HOST) {
-        uint64_t piece = (nframes + 7) / 8;
+        uint64_t piece = (nframes + 3) / 4;
         if (piece < 16) piece = 16;
         if (chunk > piece) chunk = piece;
         MDA_CUDA(pipe.init(A, same ? nullptr : B, na, nb, chunk, st));
@@ -547,7 +547,7 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     {
         uint64_t size = chunk;
         if (space == MDAGPU_HOST) {
-            size = chunk / 8;
+            size = chunk / 16;
             if (size < 16) size = 16;
             if (size > chunk) size = chunk;
         }
