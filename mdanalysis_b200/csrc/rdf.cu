@@ -475,12 +475,12 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     const bool quad = !per_site && !by_ids && W > 0 && mic == MIC_ORTHO_LAZY && r_hi > 0.0 && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max
                       && excl_a == 0 && (size_t)nbins * 4 * sizeof(uint32_t) <= 160 * 1024
                       && !getenv("MDAGPU_RDF_NO_QUAD");
-    double d_abs_err = 0.0;
+    // error of the FP32 distance estimate for the row traversals (per-cell-pair image prediction)
+    // and for the per-pair traversals the code falls back to (27-image FP32 scan for triclinic cells)
+    double err_row = 0.0, err_cell = 0.0;
     for (uint64_t f = 0; f < nbox; ++f) {
-        const double e = quad ? rowquad_abs_err(fgs[f].box, cutoff)
-                         : W  ? rowtile_abs_err(mic, fgs[f].box, cutoff)
-                              : (mic == MIC_TRICLINIC ? tric_abs_err(fgs[f].box.h) : 0.0);
-        d_abs_err = fmax(d_abs_err, e);
+        if (W) err_row = fmax(err_row, quad ? rowquad_abs_err(fgs[f].box, cutoff) : rowtile_abs_err(mic, fgs[f].box, cutoff));
+        err_cell = fmax(err_cell, mic == MIC_TRICLINIC ? tric_abs_err(fgs[f].box.h) : 0.0);
     }
 
     StagedIn thr_in, ida_in, idb_in;
@@ -497,7 +497,7 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     SearchParams sp;
     sp.d2_max = d2_max;
     sp.d2_min = -1.0;
-    sp.d2_filter = filter_threshold(d2_max, d_abs_err);
+    sp.d2_filter = 0.0f;                         // per traversal, see derive()
     sp.use_filter = mic != MIC_ORTHO_ROUND;
     sp.stencil = use_grid ? 1 : 0;
 
@@ -507,16 +507,22 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     // A band >= 0.5 disables the FP32 path.
     const float inv_dr = (float)((double)nbins / (r_hi - r_lo));
     const float c0 = (float)(-r_lo * (double)inv_dr - 0.5);
-    const double u_err = (4e-7 * fmax(fabs(r_hi), fabs(r_lo)) + d_abs_err) * (double)nbins / (r_hi - r_lo)
-                         + 2e-7 * (fabs((double)c0) + (double)nbins);
-    const float band = (float)fmax(5e-4, 2.0 * u_err);
-    // the straight-line FP32 path does not range-check the bin: it is enabled only when
-    // every pair it accepts (d2f < d2_fast_max) provably lands in [0, nbins)
-    double fast_d2 = d2_max;
-    if (r_hi > 0.0 && r_hi * r_hi < fast_d2) fast_d2 = r_hi * r_hi;
-    const bool fast_ok = r_lo <= 0.0 && r_hi > 0.0 && band < 0.25f;
-    const float band_lim = fast_ok ? 0.5f - band : -1.0f;
-    const float d2_fast_max = certain_threshold(fast_d2, d_abs_err);
+    struct Derived { float d2_filter, band_lim, d2_fast_max; };
+    auto derive = [&](double d_abs_err) {
+        Derived dv;
+        dv.d2_filter = filter_threshold(d2_max, d_abs_err);
+        const double u_err = (4e-7 * fmax(fabs(r_hi), fabs(r_lo)) + d_abs_err) * (double)nbins / (r_hi - r_lo)
+                             + 2e-7 * (fabs((double)c0) + (double)nbins);
+        const float band = (float)fmax(5e-4, 2.0 * u_err);
+        // the straight-line FP32 path does not range-check the bin: it is enabled only when
+        // every pair it accepts (d2f < d2_fast_max) provably lands in [0, nbins)
+        double fast_d2 = d2_max;
+        if (r_hi > 0.0 && r_hi * r_hi < fast_d2) fast_d2 = r_hi * r_hi;
+        const bool fast_ok = r_lo <= 0.0 && r_hi > 0.0 && band < 0.25f;
+        dv.band_lim = fast_ok ? 0.5f - band : -1.0f;
+        dv.d2_fast_max = certain_threshold(fast_d2, d_abs_err);
+        return dv;
+    };
 
     // frames are processed in chunks that keep keys 32-bit and the grid within limits
     uint64_t chunk = nframes;
@@ -656,7 +662,10 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             tv.chunks = (int)((na + threads - 1) / threads);
             tv.grid_x = (uint64_t)tv.chunks;
         }
+        const Derived dv = derive(tv.row ? err_row : err_cell);
+        const float band_lim = dv.band_lim, d2_fast_max = dv.d2_fast_max;
         SearchParams spc = sp;
+        spc.d2_filter = dv.d2_filter;
         spc.include_self = report_self;
 #define COMMA ,
 #define RUN_HIST(SINK)                                                                              \
