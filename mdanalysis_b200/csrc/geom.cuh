@@ -221,6 +221,34 @@ MDA_HD double tric_image_d2(const D3 &d, const float *h, int a, int b, int c, D3
     return img.x * img.x + img.y * img.y + img.z * img.z;
 }
 
+// The reference's loop restricted to the eight images n_k in {0, k1}, visited in the loop's own
+// order (a outermost, -1 < 0 < 1, strict '<'): when its winner is known to be one of the eight
+// (see mic_triclinic_fast8) this returns what the 27-image loop returns, near-ties included.
+MDA_HD double tric_eight_exact(const D3 &d, const float *h, int a1, int b1, int c1, D3 &img)
+{
+    double best = (double)FLT_MAX;
+    double bx = 0.0, by = 0.0, bz = 0.0;
+    for (int ia = 0; ia < 2; ++ia) {
+        const int a = (ia == 0) == (a1 < 0) ? a1 : 0;
+        double xa = d.x + (double)(h[0] * (float)a);
+        for (int ib = 0; ib < 2; ++ib) {
+            const int b = (ib == 0) == (b1 < 0) ? b1 : 0;
+            double xab = xa + (double)(h[3] * (float)b);
+            double yb = d.y + (double)(h[4] * (float)b);
+            for (int ic = 0; ic < 2; ++ic) {
+                const int c = (ic == 0) == (c1 < 0) ? c1 : 0;
+                double x = xab + (double)(h[6] * (float)c);
+                double y = yb + (double)(h[7] * (float)c);
+                double z = d.z + (double)(h[8] * (float)c);
+                double r2 = x * x + y * y + z * z;
+                if (r2 < best) { best = r2; bx = x; by = y; bz = z; }
+            }
+        }
+    }
+    img.x = bx; img.y = by; img.z = bz;
+    return best;
+}
+
 // Bit-identical to mic_triclinic(), but picks the winning image with an FP32
 // scan first; the double evaluation is done for the winner only.  If the FP32
 // scan cannot separate winner and runner-up by a safe margin (ties on lattice
@@ -296,10 +324,11 @@ MDA_HD double mic_triclinic_fast8(float tx, float ty, float tz, const BoxParams 
                 }
             }
         }
-        if (best < bp.tri_w2 && second - best > 1e-4f * second) {
+        if (best < bp.tri_w2) {
             D3 d;
             d.x = (double)tx; d.y = (double)ty; d.z = (double)tz;
-            return tric_image_d2(d, h, ba, bb, bc, out);
+            if (second - best > 1e-4f * second) return tric_image_d2(d, h, ba, bb, bc, out);
+            return tric_eight_exact(d, h, a1, b1, c1, out);
         }
     }
     return mic_triclinic_fast(tx, ty, tz, h, out);

@@ -42,6 +42,44 @@ def test_self_distance_array_bit_exact(oracle, gd, bname, n):
     assert np.array_equal(got, oracle.self_distance_array(a, BOXES[bname]))
 
 
+@pytest.mark.parametrize("bname", list(BOXES))
+@pytest.mark.parametrize("n,m", [(33, 1024), (65, 1025), (31, 2500), (40, 511)])
+def test_distance_array_tile_edges(oracle, gd, bname, n, m):
+    """Shapes around the 32 x 1024 (triclinic: 32 x 512) tile, coincident atoms (zero
+    distances take the general sqrt path) -- csrc/distances.cu da_row_values."""
+    rng = np.random.default_rng(n + m)
+    a, b = cloud(rng, n, 40, 2.0, 0.5), cloud(rng, m, 40, 2.0, 0.5)
+    b[:n:2] = a[::2]
+    assert np.array_equal(gd.distance_array(a, b, box=BOXES[bname]), oracle.distance_array(a, b, BOXES[bname]))
+    assert np.array_equal(gd.self_distance_array(b, box=BOXES[bname]), oracle.self_distance_array(b, BOXES[bname]))
+
+
+@pytest.mark.parametrize("bname", ["ortho", "tric", "tric60"])
+def test_distance_array_lattice_ties(oracle, gd, bname):
+    """Points on a lattice commensurate with the cell: many pairs have two or more images at
+    exactly the same distance (the reference keeps the first of its loop) and separations of
+    exactly half a box edge (round() half away from zero)."""
+    from mdanalysis_b200.lib.distances import _box_args
+    box = BOXES[bname]
+    h = np.asarray(_box_args(box)[1], dtype=np.float64).reshape(-1)
+    h = np.diag(h) if h.size == 3 else h.reshape(3, 3)
+    g = np.stack(np.meshgrid(*[np.arange(4)] * 3, indexing="ij"), -1).reshape(-1, 3) / 4.0
+    pts = (g @ h).astype(np.float32)
+    got = gd.distance_array(pts, pts, box=box)
+    assert np.array_equal(got, oracle.distance_array(pts, pts, box))
+    assert np.array_equal(gd.self_distance_array(pts, box=box), oracle.self_distance_array(pts, box))
+
+
+def test_distance_array_extreme_values(oracle, gd):
+    """Overflowing and tiny separations: outside the range of the in-line square root."""
+    a = np.array([[0, 0, 0], [3e38, 0, 0], [1e-30, 0, 0], [1e-45, 1e-45, 0]], dtype=np.float32)
+    b = np.array([[0, 0, 0], [-3e38, 0, 0], [-1e-30, 0, 0], [2e19, 2e19, 2e19], [1, 2, 3]], dtype=np.float32)
+    with np.errstate(all="ignore"):
+        assert np.array_equal(gd.distance_array(a, b), oracle.distance_array(a, b, None), equal_nan=True)
+        box = BOXES["ortho"]
+        assert np.array_equal(gd.distance_array(a, b, box=box), oracle.distance_array(a, b, box), equal_nan=True)
+
+
 def test_distance_array_result_argument(oracle, gd):
     rng = np.random.default_rng(1)
     a, b = cloud(rng, 50, 30), cloud(rng, 60, 30)
