@@ -203,6 +203,21 @@ MDAGPU_API int mdagpu_qcp_trajectory(const float *traj, uint64_t nframes, uint64
                           double *rot, float *aligned, int align_convention,
                           int allclose_shortcut, int space, mdagpu_stream_t stream);
 
+/* All-pairs RMSD matrix of a trajectory: analysis.diffusionmap.DistanceMatrix._single_frame
+ * (diffusionmap.py:238-268, a Python loop over frame pairs) with the metric rms.rmsd
+ * (rms.py:178-283).
+ *   traj      float32 [F, natoms, 3]
+ *   sel       int32 [nsel] indices of the atoms inside a frame, or NULL for the first nsel
+ *   weights   float64 [nsel] RELATIVE weights (divided by their mean, rms.py:270) or NULL
+ *   superposition  0: sqrt(sum(w (a - b)^2) / nsel)  (the DistanceMatrix default metric)
+ *                  1: rmsd(a, b, superposition=True): both frames centred on their weighted
+ *                     mean, then QCP (qcprot.pyx:282-543)
+ *   cutoff    entries <= cutoff are stored as 0 (diffusionmap.py:262-263)
+ *   out       float64 [F, F], symmetric (out) */
+MDAGPU_API int mdagpu_pairwise_rmsd(const float *traj, uint64_t nframes, uint64_t natoms, const int32_t *sel,
+                         uint64_t nsel, const double *weights, int superposition, double cutoff,
+                         double *out, int space, mdagpu_stream_t stream);
+
 /* ---- pair engine over many frames: InterRDF and contacts -------------------------- */
 
 /* analysis/rdf.py:268-291 for all frames at once: capped_distance(A[f], B[f], cutoff,

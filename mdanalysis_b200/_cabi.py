@@ -53,6 +53,7 @@ SIGNATURES = {
     "mdagpu_capped_bruteforce": (_i, [_vp, _u64, _vp, _u64, _d, _d, _i, _vp, _i, _vp, C.POINTER(_vp)]),
     "mdagpu_qcp": (_i, [_vp, _vp, _u64, _vp, _vp, C.POINTER(_d), _i, _vp]),
     "mdagpu_qcp_trajectory": (_i, [_vp, _u64, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mdagpu_pairwise_rmsd": (_i, [_vp, _u64, _u64, _vp, _u64, _vp, _i, _d, _vp, _i, _vp]),
     "mdagpu_rdf_accumulate": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,
                                    _d, _d, _i, _i, _vp, _i, _vp]),
     "mdagpu_rdf_accumulate_ids": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,

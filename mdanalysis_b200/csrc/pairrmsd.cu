@@ -1,0 +1,256 @@
+// pairrmsd.cu -- all-pairs RMSD matrix of a trajectory for sm_100a.
+//
+// Reference: analysis/diffusionmap.py:238-268 (DistanceMatrix._single_frame: a Python loop
+// over frame pairs, one rms.rmsd() call each) with the metric rms.rmsd, analysis/rms.py:178-283:
+//   superposition=False (the DistanceMatrix default):  sqrt(sum(w (a - b)^2) / N), float64
+//   superposition=True:  both frames centred (weighted mean), QCP (qcprot.pyx:326-543)
+//
+// One CTA owns a 32 x 32 tile of frame pairs (tiles below the diagonal are not launched: the
+// matrix is symmetric), a thread a 2 x 2 block of it.  The selected atoms are streamed through
+// shared memory in chunks of KA atoms, widened to float64 once at staging time (centred for the
+// superposition flavour, scaled by sqrt(w_k) so that the weight costs nothing in the inner loop),
+// laid out coordinate-major so that the two frames of a thread are one 16-byte load: the row
+// operand is a broadcast, the column operand is conflict-free.  Inner loop per coordinate:
+//   no fit:  d = a - b; acc = fma(d, d, acc)                  (2 FP64 ops per pair)
+//   QCP:     nine inner products a_c1 * b_c2                  (9 FP64 ops per pair and atom)
+// then one qcp_solve() per pair in the epilogue.  FP64-pipe bound; the trajectory is re-read
+// F/32 times from L2.
+#include "common.cuh"
+
+#include <vector>
+
+namespace mdagpu {
+
+constexpr int PR_T = 32;          // frames per tile side
+constexpr int PR_KA = 16;         // atoms per staged chunk
+constexpr int PR_LD = PR_T + 8;   // shared row pitch in doubles (see pair_rmsd_stage)
+constexpr int PR_THREADS = 256;   // 16 x 16 threads, 2 x 2 pairs each
+
+struct FrameCentre { double c[3]; double g; };   // weighted centroid, G = sum w |x - c|^2
+
+// per-frame weighted centroid and inner product (np.average(a, axis=0, weights=w), rms.py:262-266)
+__global__ void __launch_bounds__(256)
+pair_rmsd_centre_kernel(const float *__restrict__ traj, uint64_t natoms, const int32_t *__restrict__ sel,
+                        uint64_t nsel, const double *__restrict__ w, FrameCentre *__restrict__ out)
+{
+    const float *x = traj + (uint64_t)blockIdx.x * natoms * 3;
+    __shared__ double red[4][8];
+    __shared__ double centre[3];
+    double s[4] = { 0.0, 0.0, 0.0, 0.0 };
+    for (uint64_t k = threadIdx.x; k < nsel; k += blockDim.x) {
+        const uint64_t a = sel ? (uint64_t)sel[k] : k;
+        const double wk = w ? w[k] : 1.0;
+        s[0] += wk * (double)x[3 * a]; s[1] += wk * (double)x[3 * a + 1]; s[2] += wk * (double)x[3 * a + 2];
+        s[3] += wk;
+    }
+    for (int q = 0; q < 4; ++q) {
+        for (int o = 16; o; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = s[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0, tw = 0.0;
+        for (int i = 0; i < 8; ++i) { t += red[threadIdx.x][i]; tw += red[3][i]; }
+        centre[threadIdx.x] = t / tw;
+    }
+    __syncthreads();
+    const double cx = centre[0], cy = centre[1], cz = centre[2];
+    double g = 0.0;
+    for (uint64_t k = threadIdx.x; k < nsel; k += blockDim.x) {
+        const uint64_t a = sel ? (uint64_t)sel[k] : k;
+        const double wk = w ? w[k] : 1.0;
+        const double dx = (double)x[3 * a] - cx, dy = (double)x[3 * a + 1] - cy, dz = (double)x[3 * a + 2] - cz;
+        g += wk * (dx * dx + dy * dy + dz * dz);
+    }
+    for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = g;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[0][i];
+        out[blockIdx.x].c[0] = cx; out[blockIdx.x].c[1] = cy; out[blockIdx.x].c[2] = cz;
+        out[blockIdx.x].g = t;
+    }
+}
+
+// stage PR_KA atoms of PR_T frames: s[(atom * 3 + comp) * PR_LD + frame] = sqrt(w) * (x - centre)
+template <bool FIT>
+__device__ __forceinline__ void pair_rmsd_stage(double *s, const float *__restrict__ traj, uint64_t nframes,
+                                                uint64_t natoms, const int32_t *__restrict__ sel, uint64_t nsel,
+                                                const double *__restrict__ sqw,
+                                                const FrameCentre *__restrict__ centres, uint64_t f0, uint64_t k0)
+{
+    // a warp covers 8 frames x 4 consecutive coordinates per step: 16-byte runs of global memory,
+    // and (with rows of PR_LD doubles) conflict-free 8-byte shared stores per half warp
+    for (int e = threadIdx.x; e < PR_T * PR_KA * 3; e += PR_THREADS) {
+        const int g = e >> 5, lane = e & 31;
+        const int fr = (g & 3) * 8 + (lane & 7), kc = (g >> 2) * 4 + (lane >> 3);
+        const int ka = kc / 3, comp = kc % 3;
+        const uint64_t f = f0 + fr, k = k0 + ka;
+        double v = 0.0;
+        if (f < nframes && k < nsel) {
+            const uint64_t a = sel ? (uint64_t)sel[k] : k;
+            v = (double)traj[(f * natoms + a) * 3 + comp];
+            if (FIT) v -= centres[f].c[comp];
+            if (sqw) v *= sqw[k];
+        }
+        s[kc * PR_LD + fr] = v;
+    }
+}
+
+template <bool FIT>
+__global__ void __launch_bounds__(PR_THREADS)
+pair_rmsd_kernel(const float *__restrict__ traj, uint64_t nframes, uint64_t natoms,
+                 const int32_t *__restrict__ sel, uint64_t nsel, const double *__restrict__ sqw,
+                 const FrameCentre *__restrict__ centres, double cutoff, double *__restrict__ out)
+{
+    // upper-triangular tile index -> (ti, tj), tj >= ti
+    const unsigned nt = (unsigned)((nframes + PR_T - 1) / PR_T);
+    unsigned ti = 0, rest = blockIdx.x;
+    while (rest >= nt - ti) { rest -= nt - ti; ++ti; }
+    const unsigned tj = ti + rest;
+    const uint64_t i0 = (uint64_t)ti * PR_T, j0 = (uint64_t)tj * PR_T;
+
+    __shared__ __align__(16) double sa[PR_KA * 3 * PR_LD];
+    __shared__ __align__(16) double sb[PR_KA * 3 * PR_LD];
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;   // rows 2ty, 2ty+1; columns 2tx, 2tx+1
+
+    constexpr int NACC = FIT ? 9 : 1;
+    double acc[4][NACC];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) acc[p][q] = 0.0;
+
+    for (uint64_t k0 = 0; k0 < nsel; k0 += PR_KA) {
+        __syncthreads();
+        pair_rmsd_stage<FIT>(sa, traj, nframes, natoms, sel, nsel, sqw, centres, i0, k0);
+        if (tj != ti) pair_rmsd_stage<FIT>(sb, traj, nframes, natoms, sel, nsel, sqw, centres, j0, k0);
+        __syncthreads();
+        const double *pb = (tj != ti) ? sb : sa;
+        if constexpr (!FIT) {
+#pragma unroll 8
+            for (int kc = 0; kc < PR_KA * 3; ++kc) {
+                const double2 a = *reinterpret_cast<const double2 *>(sa + kc * PR_LD + 2 * ty);
+                const double2 b = *reinterpret_cast<const double2 *>(pb + kc * PR_LD + 2 * tx);
+                double d;
+                d = a.x - b.x; acc[0][0] = fma(d, d, acc[0][0]);
+                d = a.x - b.y; acc[1][0] = fma(d, d, acc[1][0]);
+                d = a.y - b.x; acc[2][0] = fma(d, d, acc[2][0]);
+                d = a.y - b.y; acc[3][0] = fma(d, d, acc[3][0]);
+            }
+        } else {
+#pragma unroll 2
+            for (int ka = 0; ka < PR_KA; ++ka) {
+                double2 a[3], b[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    a[c] = *reinterpret_cast<const double2 *>(sa + (ka * 3 + c) * PR_LD + 2 * ty);
+                    b[c] = *reinterpret_cast<const double2 *>(pb + (ka * 3 + c) * PR_LD + 2 * tx);
+                }
+#pragma unroll
+                for (int c1 = 0; c1 < 3; ++c1)
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; ++c2) {
+                        const int q = c1 * 3 + c2;
+                        acc[0][q] = fma(a[c1].x, b[c2].x, acc[0][q]);
+                        acc[1][q] = fma(a[c1].x, b[c2].y, acc[1][q]);
+                        acc[2][q] = fma(a[c1].y, b[c2].x, acc[2][q]);
+                        acc[3][q] = fma(a[c1].y, b[c2].y, acc[3][q]);
+                    }
+            }
+        }
+    }
+
+    const double n = (double)nsel;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const uint64_t i = i0 + 2 * ty + (p >> 1), j = j0 + 2 * tx + (p & 1);
+        if (i >= nframes || j >= nframes) continue;
+        double r;
+        if constexpr (!FIT) {
+            r = sqrt(acc[p][0] / n);
+        } else {
+            // E0 = (G_a + G_b) / 2 (qcprot.pyx:305-318), A = sum w a b^T
+            r = qcp_solve(nullptr, acc[p], 0.5 * (centres[i].g + centres[j].g), n);
+        }
+        r = r > cutoff ? r : 0.0;                 // diffusionmap.py:262-263
+        if (tj != ti) {
+            out[i * nframes + j] = r;
+            out[j * nframes + i] = r;             // diffusionmap.py:264-267
+        } else if (j >= i) {
+            // inside a diagonal tile both (i, j) and (j, i) are computed; the reference fills the
+            // lower triangle from the upper one
+            out[i * nframes + j] = r;
+            out[j * nframes + i] = r;
+        }
+    }
+}
+
+}  // namespace mdagpu
+
+using namespace mdagpu;
+
+extern "C" int mdagpu_pairwise_rmsd(const float *traj, uint64_t nframes, uint64_t natoms, const int32_t *sel,
+                                    uint64_t nsel, const double *weights, int superposition, double cutoff,
+                                    double *out, int space, mdagpu_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    MDA_REQUIRE(traj != nullptr && out != nullptr, "mdagpu_pairwise_rmsd: NULL trajectory or output");
+    MDA_REQUIRE(nsel > 0 && nsel <= natoms, "mdagpu_pairwise_rmsd: nsel must be in 1..natoms");
+    MDA_REQUIRE(sel != nullptr || nsel <= natoms, "mdagpu_pairwise_rmsd: bad selection");
+    if (nframes == 0) return MDAGPU_OK;
+    const uint64_t nt = (nframes + PR_T - 1) / PR_T;
+    MDA_REQUIRE(nt * (nt + 1) / 2 <= 0x7fffffffull, "mdagpu_pairwise_rmsd: too many frames (%llu)",
+                (unsigned long long)nframes);
+    StagedIn t, s, w;
+    StagedOut o;
+    MDA_CUDA(t.init(traj, nframes * natoms * 3 * sizeof(float), space, st));
+    MDA_CUDA(s.init(sel, nsel * sizeof(int32_t), space, st));
+    MDA_CUDA(o.init(out, nframes * nframes * sizeof(double), space, st));
+    // sqrt of the relative weights: always prepared on the host (nsel doubles)
+    DevBuf sqw;
+    std::vector<double> hw;
+    const double *w_dev = nullptr;
+    if (weights) {
+        hw.resize(nsel);
+        if (space == MDAGPU_DEVICE)
+            MDA_CUDA(cudaMemcpyAsync(hw.data(), weights, nsel * sizeof(double), cudaMemcpyDeviceToHost, st));
+        else
+            memcpy(hw.data(), weights, nsel * sizeof(double));
+        MDA_CUDA(cudaStreamSynchronize(st));
+        MDA_CUDA(w.init(hw.data(), nsel * sizeof(double), MDAGPU_HOST, st));   // plain weights for the centroids
+        w_dev = w.as<double>();
+    }
+    std::vector<double> hs;
+    if (weights) {
+        hs.resize(nsel);
+        for (uint64_t k = 0; k < nsel; ++k) {
+            MDA_REQUIRE(hw[k] >= 0.0, "mdagpu_pairwise_rmsd: negative weight");
+            hs[k] = sqrt(hw[k]);
+        }
+        MDA_CUDA(sqw.alloc(nsel * sizeof(double), st));
+        MDA_CUDA(cudaMemcpyAsync(sqw.p, hs.data(), nsel * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    DevBuf centres;
+    if (superposition) {
+        MDA_CUDA(centres.alloc(nframes * sizeof(FrameCentre), st));
+        MDA_LAUNCH(pair_rmsd_centre_kernel, (unsigned)nframes, 256, 0, st, t.as<float>(), natoms, s.as<int32_t>(), nsel,
+                   w_dev, centres.as<FrameCentre>());
+        MDA_CHECK_LAUNCH();
+    }
+    const unsigned grid = (unsigned)(nt * (nt + 1) / 2);
+    if (superposition)
+        MDA_LAUNCH_AS("pair_rmsd_kernel", pair_rmsd_kernel<true>, grid, PR_THREADS, 0, st, t.as<float>(), nframes, natoms,
+                      s.as<int32_t>(), nsel, weights ? sqw.as<double>() : nullptr, centres.as<FrameCentre>(), cutoff,
+                      o.as<double>());
+    else
+        MDA_LAUNCH_AS("pair_rmsd_kernel", pair_rmsd_kernel<false>, grid, PR_THREADS, 0, st, t.as<float>(), nframes, natoms,
+                      s.as<int32_t>(), nsel, weights ? sqw.as<double>() : nullptr, (const FrameCentre *)nullptr, cutoff,
+                      o.as<double>());
+    MDA_CHECK_LAUNCH();
+    MDA_CUDA(o.finish());
+    MDA_CUDA(cudaStreamSynchronize(st));   // host-side weight buffers are sources of async copies
+    return MDAGPU_OK;
+}

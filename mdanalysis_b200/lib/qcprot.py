@@ -97,3 +97,44 @@ def qcp_trajectory(traj, reference, select=None, weights=None, want_rotation=Fal
                                     ptr(rot), ptr(dst), int(convention),
                                     int(bool(allclose_shortcut)), HOST, None))
     return rmsd, rot, dst
+
+
+def pairwise_rmsd(traj, select=None, weights=None, superposition=False, cutoff=-4.0):
+    """RMSD between every pair of frames in one launch (``mdagpu_pairwise_rmsd``):
+    ``rms.rmsd(traj[i, select], traj[j, select], weights, superposition=superposition)`` for all
+    i, j -- the loop of ``diffusionmap.DistanceMatrix._single_frame`` (diffusionmap.py:248-267).
+
+    traj     float32 [F, natoms, 3] NumPy array or torch CUDA tensor
+    weights  any non-negative weights over the selected atoms (normalised here by their mean,
+             rms.py:270) or None
+    Returns the symmetric float64 [F, F] matrix, of the input kind."""
+    dev = is_tensor(traj)
+    F, natoms = int(traj.shape[0]), int(traj.shape[1])
+    if tuple(traj.shape[2:]) != (3,):
+        raise ValueError(f"traj must have shape (F, n, 3), got {tuple(traj.shape)}")
+    sel = None if select is None else np.ascontiguousarray(select, dtype=np.int32)
+    nsel = natoms if sel is None else len(sel)
+    if sel is not None and nsel and (sel.min() < 0 or sel.max() >= natoms):
+        raise IndexError("selection index out of range")
+    w = None
+    if weights is not None:
+        w = np.asarray(weights, dtype=np.float64)
+        if w.shape != (nsel,):
+            raise ValueError("weights must have same length as a and b")
+        w = np.ascontiguousarray(w / np.mean(w))
+    lib = load()
+    if dev:
+        import torch
+        t = traj if (traj.dtype == torch.float32 and traj.is_contiguous()) else traj.to(torch.float32).contiguous()
+        out = torch.zeros((F, F), dtype=torch.float64, device=t.device)
+        sel_d = None if sel is None else torch.as_tensor(sel, device=t.device)
+        w_d = None if w is None else torch.as_tensor(w, device=t.device)
+        check(lib.mdagpu_pairwise_rmsd(tensor_ptr(t), F, natoms, tensor_ptr(sel_d), nsel, tensor_ptr(w_d),
+                                       int(bool(superposition)), float(cutoff), tensor_ptr(out), DEVICE,
+                                       current_stream(t)))
+        return out
+    t = np.ascontiguousarray(traj, dtype=np.float32)
+    out = np.zeros((F, F), dtype=np.float64)
+    check(lib.mdagpu_pairwise_rmsd(ptr(t), F, natoms, ptr(sel), nsel, ptr(w), int(bool(superposition)),
+                                   float(cutoff), ptr(out), HOST, None))
+    return out

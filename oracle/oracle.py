@@ -583,6 +583,22 @@ def rmsd(a, b, weights=None, center=False, superposition=False):
     return np.sqrt(np.sum((a - b) ** 2) / N)
 
 
+def distance_matrix(traj, select=None, weights=None, superposition=False, cutoff=1E0 - 5):
+    """analysis/diffusionmap.py:238-268: DistanceMatrix with metric = rms.rmsd (optionally with
+    superposition=True), as the reference's own double loop over frame pairs."""
+    traj = np.asarray(traj, dtype=np.float32)
+    if select is not None:
+        traj = traj[:, np.asarray(select)]
+    F = traj.shape[0]
+    m = np.zeros((F, F))
+    for i in range(F):
+        for j in range(i, F):
+            d = rmsd(traj[i], traj[j], weights=weights, superposition=superposition)
+            m[i, j] = d if d > cutoff else 0
+            m[j, i] = m[i, j]
+    return m
+
+
 def _center(xyz_f32, weights):
     """core/groups.py:1083-1106, compound='group'."""
     if weights is None:
