@@ -350,6 +350,17 @@ def secondary_benchmarks(torch, hbm_peak, peak_kind, quick):
     out["aligntraj_qcp"] = {"frames_per_s": Fq / ms * 1e3, "ms": ms,
                             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                          "frac": gbs / hbm_peak, "peak_kind": peak_kind}}
+    # section 8f: all-pairs RMSD matrix (diffusionmap.DistanceMatrix) of the first frames of the same trajectory
+    Fp = 2048 if not quick else 256
+    fp64_peak = 61.4 * 148 * 1.965e9 / 1e12      # T lane-ops/s, DFMA rate of profiles/microbench/pipes_b200.txt
+    for label, sup, ops in (("pairwise_rmsd", False, 2 * 3), ("pairwise_rmsd_superposed", True, 9)):
+        ms = timed(lambda: qcprot.pairwise_rmsd(traj[:Fp], superposition=sup), 3)
+        npair = Fp * (Fp + 1) // 2
+        tops = npair * na * ops / ms / 1e9
+        out[label] = {"frame_pairs_per_s": npair / ms * 1e3, "ms": ms, "shape": [Fp, na, 3],
+                      "roofline": {"bound": "fp64", "achieved": tops, "peak": fp64_peak, "unit": "T FP64 lane-ops/s",
+                                   "frac": tops / fp64_peak, "peak_kind": "measured DFMA issue rate (61.4 lanes/clk/SM at 1965 MHz)",
+                                   "note": f"{ops} FP64 instructions per frame pair and atom"}}
     del traj
     torch.cuda.empty_cache()
 

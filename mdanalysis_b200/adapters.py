@@ -16,7 +16,8 @@ What happens: the frames of the AtomGroups are read in bulk (``FrameBlock.from_a
 from the attributes the reference constructor left on the object, all frames go through the
 CUDA kernels in one call, and ``results`` / ``frames`` / ``times`` / ``n_frames`` are written
 back onto the reference object.  Supported: ``rdf.InterRDF``, ``rdf.InterRDF_s``, ``rms.RMSD``,
-``align.AlignTraj`` and ``align.AverageStructure`` (in-memory trajectories), ``contacts.Contacts``.
+``align.AlignTraj`` and ``align.AverageStructure`` (in-memory trajectories), ``contacts.Contacts``,
+``diffusionmap.DistanceMatrix`` (metric ``rms.rmsd``, optionally ``partial(rmsd, superposition=True)``).
 """
 from __future__ import annotations
 
@@ -179,7 +180,19 @@ def _run_contacts(an, idx, device):
     return an
 
 
-_RUNNERS = {"InterRDF": _run_interrdf, "InterRDF_s": _run_interrdf_s, "RMSD": _run_rmsd,
+def _run_distance_matrix(an, idx, device):
+    """diffusionmap.DistanceMatrix (diffusionmap.py:226-289): atoms, _metric, _cutoff, _weights."""
+    from .analysis.diffusionmap import DistanceMatrix
+    blk = _block(an.atoms, idx)
+    if device:
+        blk = blk.to_device()
+    gpu = DistanceMatrix(blk, metric=an._metric, cutoff=an._cutoff, weights=an._weights).run()
+    an.results.dist_matrix = gpu.results.dist_matrix
+    an._calculated = True
+    return _finish(an, gpu)
+
+
+_RUNNERS = {"InterRDF": _run_interrdf, "DistanceMatrix": _run_distance_matrix, "InterRDF_s": _run_interrdf_s, "RMSD": _run_rmsd,
             "AlignTraj": _run_aligntraj, "AverageStructure": _run_average_structure, "Contacts": _run_contacts}
 
 

@@ -321,3 +321,39 @@ def test_average_structure_against_reference(mda):
     g = AverageStructure(FrameBlock(traj.copy(), masses=masses), FrameBlock(ref_xyz.astype(np.float32)[None], masses=masses),
                          select=idx, weights="mass").run()
     assert np.allclose(g.results.positions, want.results.positions, rtol=0, atol=2e-5)
+
+
+def test_distance_matrix_against_reference(mda):
+    """diffusionmap.DistanceMatrix of the real reference (a Python loop over frame pairs) next to the
+    GPU class and to run_on_gpu on the reference object; plain and superposed metric, weights, frames=."""
+    import functools
+
+    from MDAnalysis.analysis import diffusionmap as rdm
+    from MDAnalysis.analysis.rms import rmsd as ref_rmsd
+    from mdanalysis_b200 import run_on_gpu
+    from mdanalysis_b200.analysis.diffusionmap import DistanceMatrix, rmsd_superposition
+    rng = np.random.default_rng(14)
+    F, N = 37, 150
+    base = rng.normal(0, 9, (N, 3))
+    traj = np.stack([(base @ np.linalg.qr(rng.normal(size=(3, 3)))[0] + rng.normal(0, 3, 3)
+                      + rng.normal(0, 0.8, (N, 3))) for _ in range(F)]).astype(np.float32)
+    w = rng.uniform(1, 32, N)
+    fit = functools.partial(ref_rmsd, superposition=True)
+    for metric, gpu_metric, weights, tol in ((ref_rmsd, ref_rmsd, None, 0.0), (ref_rmsd, ref_rmsd, w, 0.0),
+                                             (fit, rmsd_superposition, None, 5e-6), (fit, fit, w, 5e-6)):
+        want = rdm.DistanceMatrix(_universe(mda, traj, None), metric=metric, weights=weights).run().results.dist_matrix
+        got = DistanceMatrix(traj, metric=gpu_metric, weights=weights).run().results.dist_matrix
+        np.testing.assert_allclose(got, want, rtol=1e-7, atol=tol)
+        obj = run_on_gpu(rdm.DistanceMatrix(_universe(mda, traj, None), metric=metric, weights=weights))
+        np.testing.assert_allclose(obj.results.dist_matrix, want, rtol=1e-7, atol=tol)
+        assert obj.n_frames == F and obj._calculated
+    frames = [3, 4, 9, 30]
+    want = rdm.DistanceMatrix(_universe(mda, traj, None), select="index 0:99").run(frames=frames).results.dist_matrix
+    got = run_on_gpu(rdm.DistanceMatrix(_universe(mda, traj, None), select="index 0:99"), frames=frames)
+    np.testing.assert_allclose(got.results.dist_matrix, want, rtol=1e-9)
+    # the reference's DiffusionMap runs on top of a matrix computed here
+    dmap = rdm.DiffusionMap(run_on_gpu(rdm.DistanceMatrix(_universe(mda, traj, None))), epsilon=2.0)
+    dmap.run()
+    ref_map = rdm.DiffusionMap(_universe(mda, traj, None), epsilon=2.0)
+    ref_map.run()
+    np.testing.assert_allclose(dmap.eigenvalues, ref_map.eigenvalues, rtol=1e-6, atol=1e-9)
