@@ -74,33 +74,61 @@ pair_rmsd_centre_kernel(const float *__restrict__ traj, uint64_t natoms, const i
     }
 }
 
-// stage PR_KA atoms of PR_T frames: s[(atom * 3 + comp) * PR_LD + frame] = sqrt(w) * (x - centre)
-template <bool FIT>
-__device__ __forceinline__ void pair_rmsd_stage(double *s, const float *__restrict__ traj, uint64_t nframes,
-                                                uint64_t natoms, const int32_t *__restrict__ sel, uint64_t nsel,
-                                                const double *__restrict__ sqw,
-                                                const FrameCentre *__restrict__ centres, uint64_t f0, uint64_t k0)
-{
-    // a warp covers 8 frames x 4 consecutive coordinates per step: 16-byte runs of global memory,
-    // and (with rows of PR_LD doubles) conflict-free 8-byte shared stores per half warp
-    for (int e = threadIdx.x; e < PR_T * PR_KA * 3; e += PR_THREADS) {
-        const int g = e >> 5, lane = e & 31;
-        const int fr = (g & 3) * 8 + (lane & 7), kc = (g >> 2) * 4 + (lane >> 3);
-        const int ka = kc / 3, comp = kc % 3;
-        const uint64_t f = f0 + fr, k = k0 + ka;
-        double v = 0.0;
-        if (f < nframes && k < nsel) {
-            const uint64_t a = sel ? (uint64_t)sel[k] : k;
-            v = (double)traj[(f * natoms + a) * 3 + comp];
-            if (FIT) v -= centres[f].c[comp];
-            if (sqw) v *= sqw[k];
-        }
-        s[kc * PR_LD + fr] = v;
+// Staging.  A thread always serves the same frame of the tile and the same six coordinate slots
+// of a chunk (slot = kc0 + 8 r): a warp step covers 8 frames x 4 consecutive coordinates (16-byte
+// runs of global memory) and, with rows of PR_LD doubles, its 8-byte shared stores are
+// conflict-free per half warp.  The values of the NEXT chunk are fetched into registers before
+// the current chunk is computed, so the global-load latency is covered by the arithmetic.
+constexpr int PR_SLOTS = PR_T * PR_KA * 3 / PR_THREADS;   // 6 per operand and thread
+
+struct PairStager {
+    const float *row;       // first coordinate of the thread's frame (nullptr: frame outside the trajectory)
+    int fr, kc0;
+    const double *c;        // centroid of the frame (superposition flavour), read when needed
+    __device__ __forceinline__ void init(const float *traj, uint64_t nframes, uint64_t natoms, uint64_t f0,
+                                         const FrameCentre *centres)
+    {
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        fr = (w & 3) * 8 + (lane & 7);
+        kc0 = (w >> 2) * 4 + (lane >> 3);
+        const uint64_t f = f0 + fr;
+        row = f < nframes ? traj + f * natoms * 3 : nullptr;
+        c = (centres && row) ? centres[f].c : nullptr;
     }
-}
+    // raw float32 values of chunk k0 (0 outside the selection / trajectory)
+    __device__ __forceinline__ void fetch(float (&v)[PR_SLOTS], const int32_t *__restrict__ sel, uint64_t nsel,
+                                          uint64_t k0) const
+    {
+#pragma unroll
+        for (int r = 0; r < PR_SLOTS; ++r) {
+            const int kc = kc0 + 8 * r;
+            const uint64_t k = k0 + kc / 3;
+            v[r] = 0.0f;
+            if (row && k < nsel) v[r] = sel ? row[(uint64_t)sel[k] * 3 + kc % 3] : row[k0 * 3 + kc];
+        }
+    }
+    // s[(atom * 3 + comp) * PR_LD + frame] = sqrt(w) * (x - centre)
+    template <bool FIT>
+    __device__ __forceinline__ void store(double *s, const float (&v)[PR_SLOTS], const double *__restrict__ sqw,
+                                          uint64_t nsel, uint64_t k0) const
+    {
+#pragma unroll
+        for (int r = 0; r < PR_SLOTS; ++r) {
+            const int kc = kc0 + 8 * r;
+            const uint64_t k = k0 + kc / 3;
+            double x = 0.0;
+            if (row && k < nsel) {
+                x = (double)v[r];
+                if (FIT) x -= c[kc % 3];
+                if (sqw) x *= sqw[k];
+            }
+            s[kc * PR_LD + fr] = x;
+        }
+    }
+};
 
 template <bool FIT>
-__global__ void __launch_bounds__(PR_THREADS)
+__global__ void __launch_bounds__(PR_THREADS, FIT ? 2 : 3)
 pair_rmsd_kernel(const float *__restrict__ traj, uint64_t nframes, uint64_t natoms,
                  const int32_t *__restrict__ sel, uint64_t nsel, const double *__restrict__ sqw,
                  const FrameCentre *__restrict__ centres, double cutoff, double *__restrict__ out)
@@ -111,6 +139,7 @@ pair_rmsd_kernel(const float *__restrict__ traj, uint64_t nframes, uint64_t nato
     while (rest >= nt - ti) { rest -= nt - ti; ++ti; }
     const unsigned tj = ti + rest;
     const uint64_t i0 = (uint64_t)ti * PR_T, j0 = (uint64_t)tj * PR_T;
+    const bool offdiag = tj != ti;
 
     __shared__ __align__(16) double sa[PR_KA * 3 * PR_LD];
     __shared__ __align__(16) double sb[PR_KA * 3 * PR_LD];
@@ -123,17 +152,37 @@ pair_rmsd_kernel(const float *__restrict__ traj, uint64_t nframes, uint64_t nato
 #pragma unroll
         for (int q = 0; q < NACC; ++q) acc[p][q] = 0.0;
 
+    PairStager sta, stb;
+    sta.init(traj, nframes, natoms, i0, FIT ? centres : nullptr);
+    stb.init(traj, nframes, natoms, j0, FIT ? centres : nullptr);
+    // the nine-accumulator flavour has no registers to spare: it fetches just before it stores
+    constexpr bool PREFETCH = !FIT;
+    float va[PR_SLOTS], vb[PR_SLOTS];
+    if (PREFETCH) {
+        sta.fetch(va, sel, nsel, 0);
+        if (offdiag) stb.fetch(vb, sel, nsel, 0);
+    }
+    const double *pa = sa + 2 * ty;
+    const double *pb = (offdiag ? sb : sa) + 2 * tx;
+
     for (uint64_t k0 = 0; k0 < nsel; k0 += PR_KA) {
+        if (!PREFETCH) {
+            sta.fetch(va, sel, nsel, k0);
+            if (offdiag) stb.fetch(vb, sel, nsel, k0);
+        }
+        __syncthreads();                       // the previous chunk has been consumed
+        sta.template store<FIT>(sa, va, sqw, nsel, k0);
+        if (offdiag) stb.template store<FIT>(sb, vb, sqw, nsel, k0);
         __syncthreads();
-        pair_rmsd_stage<FIT>(sa, traj, nframes, natoms, sel, nsel, sqw, centres, i0, k0);
-        if (tj != ti) pair_rmsd_stage<FIT>(sb, traj, nframes, natoms, sel, nsel, sqw, centres, j0, k0);
-        __syncthreads();
-        const double *pb = (tj != ti) ? sb : sa;
+        if (PREFETCH && k0 + PR_KA < nsel) {   // in flight while this chunk is computed
+            sta.fetch(va, sel, nsel, k0 + PR_KA);
+            if (offdiag) stb.fetch(vb, sel, nsel, k0 + PR_KA);
+        }
         if constexpr (!FIT) {
 #pragma unroll 8
             for (int kc = 0; kc < PR_KA * 3; ++kc) {
-                const double2 a = *reinterpret_cast<const double2 *>(sa + kc * PR_LD + 2 * ty);
-                const double2 b = *reinterpret_cast<const double2 *>(pb + kc * PR_LD + 2 * tx);
+                const double2 a = *reinterpret_cast<const double2 *>(pa + kc * PR_LD);
+                const double2 b = *reinterpret_cast<const double2 *>(pb + kc * PR_LD);
                 double d;
                 d = a.x - b.x; acc[0][0] = fma(d, d, acc[0][0]);
                 d = a.x - b.y; acc[1][0] = fma(d, d, acc[1][0]);
@@ -146,8 +195,8 @@ pair_rmsd_kernel(const float *__restrict__ traj, uint64_t nframes, uint64_t nato
                 double2 a[3], b[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    a[c] = *reinterpret_cast<const double2 *>(sa + (ka * 3 + c) * PR_LD + 2 * ty);
-                    b[c] = *reinterpret_cast<const double2 *>(pb + (ka * 3 + c) * PR_LD + 2 * tx);
+                    a[c] = *reinterpret_cast<const double2 *>(pa + (ka * 3 + c) * PR_LD);
+                    b[c] = *reinterpret_cast<const double2 *>(pb + (ka * 3 + c) * PR_LD);
                 }
 #pragma unroll
                 for (int c1 = 0; c1 < 3; ++c1)
@@ -176,7 +225,7 @@ pair_rmsd_kernel(const float *__restrict__ traj, uint64_t nframes, uint64_t nato
             r = qcp_solve(nullptr, acc[p], 0.5 * (centres[i].g + centres[j].g), n);
         }
         r = r > cutoff ? r : 0.0;                 // diffusionmap.py:262-263
-        if (tj != ti) {
+        if (offdiag) {
             out[i * nframes + j] = r;
             out[j * nframes + i] = r;             // diffusionmap.py:264-267
         } else if (j >= i) {
