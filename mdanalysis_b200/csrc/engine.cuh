@@ -334,6 +334,30 @@ struct PairSink {
     template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t f) { hit(i, j, d2, f); }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void end() {}
+    __device__ __forceinline__ void put(unsigned long long slot, int i, int j, double d2)
+    {
+        if (slot < capacity) {
+            longlong2 p;
+            p.x = i; p.y = j;
+            if (orient && i > j) { p.x = j; p.y = i; }
+            *reinterpret_cast<longlong2 *>(pairs + 2 * slot) = p;
+            dist[slot] = sqrt(d2);
+        }
+    }
+    // two candidates per lane, all 32 lanes converged: one atomic for both rounds
+    __device__ __forceinline__ void hit2(bool h0, int i0, int j0, double d0, bool h1, int i1, int j1, double d1)
+    {
+        const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+        const int n0 = __popc(m0), n1 = __popc(m1);
+        if (n0 + n1 == 0) return;
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)(n0 + n1));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (h0) put(base + __popc(m0 & lt), i0, j0, d0);
+        if (h1) put(base + n0 + __popc(m1 & lt), i1, j1, d1);
+    }
     __device__ __forceinline__ void hit(int i, int j, double d2, uint64_t)
     {
         const unsigned m = __activemask();

@@ -303,7 +303,8 @@ static int run_pair_search(const CellList &ql, uint64_t nq, const CellList &cl,
         PairSink sink = { res->pairs, res->dist, counter.as<unsigned long long>(), cap, orient };
         if constexpr (MIC != MIC_ORTHO_ROUND) if (tv.row) {
             dim3 grid((unsigned)tv.grid_x, 1);
-            MDA_LAUNCH_AS(SELF ? "pair_self_search" : "pair_search", (row_pairs_kernel<MIC, SELF, PairSink>), grid, PairSink::THREADS, 0, st,
+            MDA_CUDA(cudaFuncSetAttribute(row_pairs_kernel<MIC, SELF, PairSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_DYN_BYTES));
+            MDA_LAUNCH_AS(SELF ? "pair_self_search" : "pair_search", (row_pairs_kernel<MIC, SELF, PairSink>), grid, PairSink::THREADS, RP_DYN_BYTES, st,
                        ql.atoms(), ql.start(), cl.atoms(), cl.start(), fg_dev, 0, tv.rp, sp, sink);
         }
         if (!tv.row || MIC == MIC_ORTHO_ROUND) {

@@ -14,15 +14,23 @@
 //   * whenever 32 are queued, all 32 lanes evaluate one each with the reference's float64
 //     arithmetic (the image predicted for the cell pair, geom.cuh) and append the accepted
 //     ones through the sink (warp-aggregated global atomic, engine.cuh PairSink).
-// Staging: the candidates of a stencil row (float4 {x, y, z, index}) are copied to shared
-// memory by all threads, two buffers, one __syncthreads per row.
+// Staging.  When all stencil rows of the CTA fit (RP_ALL candidates; 1 M atoms at 0.1 / A^3 and an
+// 8 A cutoff: 14 rows x ~234), they are staged ONCE as x / y / z planes and every warp then
+// runs through its rows on its own: with one __syncthreads per row the warps that had just
+// drained their queue arrived late and everybody else waited (ncu: 4.2 barrier-stalled warps
+// per issue, 39 % issue use).  The planes also feed FOUR candidates per trip (three LDS.128,
+// four ballots, one branch).  Rows that do not fit are staged one at a time as float4
+// {x, y, z, index}, two buffers, one __syncthreads per row.
 #pragma once
 #include "rowtile.cuh"
 
 namespace mdagpu {
 
-constexpr int RP_TILE = 1024;             // staged candidates per buffer
+constexpr int RP_TILE = 1024;             // staged candidates per buffer (row-by-row path)
+constexpr int RP_ALL = 3584;              // staged candidates of ALL rows (plane path): 3 x 14 kB
 constexpr int RP_QUEUE = 96;              // queued survivors per warp (drained at >= 32)
+constexpr size_t RP_DYN_BYTES = 3 * (RP_ALL + 4) * sizeof(float);   // >= 2 * RP_TILE * sizeof(float4)
+static_assert(RP_DYN_BYTES >= 2 * RP_TILE * sizeof(float4), "the row-by-row buffers live in the same allocation");
 
 template <int MIC, bool SELF, class Sink>
 __global__ void __launch_bounds__(Sink::THREADS)
@@ -32,7 +40,9 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
 {
     constexpr int T = Sink::THREADS, NW = T / 32;
     __shared__ RowBook bk;
-    __shared__ __align__(16) float4 tile[2][RP_TILE];
+    extern __shared__ __align__(16) unsigned char rp_dyn[];         // RP_DYN_BYTES
+    float4 (*tile)[RP_TILE] = reinterpret_cast<float4 (*)[RP_TILE]>(rp_dyn);
+    __shared__ uint32_t s_rowbase[ROW_MAXROWS + 1];
     __shared__ uint32_t s_qq[NW][RP_QUEUE], s_qc[NW][RP_QUEUE];
     __shared__ uint8_t s_qi[NW][RP_QUEUE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -94,6 +104,149 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
         }
     };
 
+    // ---- plane path: every row staged once ------------------------------------------------
+    if (tid == 0) {
+        uint32_t b0 = 0;
+        for (int r = 0; r < nrows; ++r) { s_rowbase[r] = b0; b0 += bk.row[r].end[2]; }
+        s_rowbase[nrows] = b0;
+    }
+    __syncthreads();
+    if (s_rowbase[nrows] <= (uint32_t)RP_ALL) {
+        float *px = reinterpret_cast<float *>(rp_dyn), *py = px + (RP_ALL + 4), *pz = py + (RP_ALL + 4);
+        for (int r = 0; r < nrows; ++r) {
+            const RowInfo &ri = bk.row[r];
+            const uint32_t rb = s_rowbase[r];
+            for (uint32_t t = tid; t < ri.end[2]; t += T) {
+                const int s = t >= ri.end[1] ? 2 : (t >= ri.end[0] ? 1 : 0);
+                const float4 c = c_atoms[ri.g[s] + (t - (s ? ri.end[s - 1] : 0u))];
+                px[rb + t] = c.x; py[rb + t] = c.y; pz[rb + t] = c.z;
+            }
+        }
+        if (tid < 4) {                                              // the last quad may read past the end
+            const uint32_t e = s_rowbase[nrows] + tid;
+            px[e] = py[e] = pz[e] = 1.0e18f;
+        }
+        __syncthreads();
+        for (uint32_t qbase = qs0; qbase < qs1; qbase += T) {
+            const uint32_t qslot = qbase + tid;
+            const bool active = qslot < qs1;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            int cxl = 0;
+            if (active) {
+                q = q_atoms[qslot];
+                while (cxl + 1 < nh && bk.qst[cxl + 1] <= qslot) ++cxl;
+            }
+            if (SELF && sp.include_self && active) {
+                const double d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, q.x, q.y, q.z, box);
+                if (d2 <= sp.d2_max && d2 > sp.d2_min) sink.template hit_w<false>(__float_as_int(q.w), __float_as_int(q.w), d2, f);
+            }
+            const int cmin = (int)__reduce_min_sync(0xffffffffu, active ? (unsigned)cxl : 0x7fffffffu);
+            const int cmax = (int)__reduce_max_sync(0xffffffffu, active ? (unsigned)cxl : 0u);
+            if (cmin == 0x7fffffff) continue;                       // no query in this warp (uniform)
+            // float64 evaluation of up to 64 queued survivors, two per lane: the queue names the lane
+            // that owns the query (a shuffle instead of a gather), both candidates are fetched before
+            // either is used, and the accepted pairs of both rounds share one atomic
+            auto drain = [&](uint32_t first, uint32_t count) {
+                __syncwarp();
+                const bool v0 = (uint32_t)lane < count, v1 = (uint32_t)lane + 32u < count;
+                const uint32_t e0 = first + lane, e1 = e0 + 32u;
+                const uint32_t l0 = v0 ? qq[e0] : 0u, l1 = v1 ? qq[e1] : 0u;
+                const int code0 = v0 ? qi[e0] : 0, code1 = v1 ? qi[e1] : 0;
+                float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                if (v0) c0 = c_atoms[qc[e0]];
+                if (v1) c1 = c_atoms[qc[e1]];
+                float4 q0, q1;
+                q0.x = __shfl_sync(0xffffffffu, q.x, l0); q0.y = __shfl_sync(0xffffffffu, q.y, l0);
+                q0.z = __shfl_sync(0xffffffffu, q.z, l0); q0.w = __shfl_sync(0xffffffffu, q.w, l0);
+                q1.x = __shfl_sync(0xffffffffu, q.x, l1); q1.y = __shfl_sync(0xffffffffu, q.y, l1);
+                q1.z = __shfl_sync(0xffffffffu, q.z, l1); q1.w = __shfl_sync(0xffffffffu, q.w, l1);
+                auto exact = [&](const float4 &qa, const float4 &ca, int code) {
+                    if (MIC == MIC_TRICLINIC) {
+                        D3 d = sep_f32(qa.x, qa.y, qa.z, ca.x, ca.y, ca.z), img;
+                        return tric_image_d2(d, box.h, (code & 3) - 1, -(((code >> 2) & 3) - 1), -(((code >> 4) & 3) - 1), img);
+                    }
+                    return pair_d2_exact<MIC>(qa.x, qa.y, qa.z, ca.x, ca.y, ca.z, box);
+                };
+                const double d0 = exact(q0, c0, code0), d1 = exact(q1, c1, code1);
+                sink.hit2(v0 && d0 <= sp.d2_max && d0 > sp.d2_min, __float_as_int(q0.w), __float_as_int(c0.w), d0,
+                          v1 && d1 <= sp.d2_max && d1 > sp.d2_min, __float_as_int(q1.w), __float_as_int(c1.w), d1);
+                __syncwarp();
+            };
+            for (int r = 0; r < nrows; ++r) {
+                const RowInfo &ri = bk.row[r];
+                if (ri.end[2] == 0u) continue;
+                const bool home = SELF && r == 0;
+                const int ncell = home ? nh + W : NC;
+                const int span = home ? W : 2 * W;
+                uint32_t lo = 0, hi = 0;
+                if (active) {
+                    lo = bk.off[r][cxl];
+                    hi = bk.off[r][min(cxl + span + 1, ncell)];
+                    if (home) lo += (qslot - bk.qst[cxl]) + 1;
+                }
+                const uint32_t wlo = bk.off[r][cmin], whi = bk.off[r][min(cmax + span + 1, ncell)];
+                const float qrx = q.x - ((float)ri.ib * hy[0] + (float)ri.ic * hz[0]);
+                const float qry = q.y - ((float)ri.ib * hy[1] + (float)ri.ic * hz[1]);
+                const float qrz = q.z - ((float)ri.ib * hy[2] + (float)ri.ic * hz[2]);
+                const uint32_t rb = s_rowbase[r];
+                uint32_t sb = 0;
+#pragma unroll 1
+                for (int s = 0; s < 3; ++s) {
+                    const uint32_t se = ri.end[s];
+                    const uint32_t a = max(wlo, sb), e = min(whi, se);      // warp-uniform
+                    if (a < e) {
+                        const float sgn = (float)(1 - s);
+                        const float qx = qrx + sgn * hx[0], qy = qry + sgn * hx[1], qz = qrz + sgn * hx[2];
+                        const uint32_t code = (uint32_t)((1 - s) + 1) | (uint32_t)(ri.ib + 1) << 2 | (uint32_t)(ri.ic + 1) << 4;
+                        const uint32_t gbase = ri.g[s] - sb;
+                        // the lane's own part of this run as (first, width) for one unsigned compare
+                        const uint32_t lo2 = max(lo, a), hi2 = min(hi, e);
+                        const uint32_t width = hi2 > lo2 ? hi2 - lo2 : 0u;
+                        for (uint32_t qd = (rb + a) & ~3u; qd < rb + e; qd += 4u) {
+                            const float4 X = *reinterpret_cast<const float4 *>(px + qd);
+                            const float4 Y = *reinterpret_cast<const float4 *>(py + qd);
+                            const float4 Z = *reinterpret_cast<const float4 *>(pz + qd);
+                            const uint32_t rel = qd - rb - lo2;     // row coordinate of candidate 0, minus lo2 (mod 2^32)
+                            const float cxs[4] = { X.x, X.y, X.z, X.w }, cys[4] = { Y.x, Y.y, Y.z, Y.w }, czs[4] = { Z.x, Z.y, Z.z, Z.w };
+                            uint32_t m[4];
+                            bool keep[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float tx = qx - cxs[k], ty = qy - cys[k], tz = qz - czs[k];
+                                const float d2f = fmaf(tx, tx, fmaf(ty, ty, tz * tz));
+                                keep[k] = d2f <= sp.d2_filter && rel + (uint32_t)k < width;
+                                m[k] = __ballot_sync(0xffffffffu, keep[k]);
+                            }
+                            if (m[0] | m[1] | m[2] | m[3]) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (m[k] == 0u) continue;
+                                    if (keep[k]) {
+                                        const uint32_t at = nqueued + __popc(m[k] & ((1u << lane) - 1u));
+                                        qq[at] = (uint32_t)lane;
+                                        qc[at] = gbase + (qd - rb) + (uint32_t)k;
+                                        qi[at] = (uint8_t)code;
+                                    }
+                                    nqueued += __popc(m[k]);
+                                    if (nqueued >= 64u) {
+                                        drain(nqueued - 64u, 64u);
+                                        nqueued -= 64u;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    sb = se;
+                }
+            }
+            if (nqueued) drain(0u, nqueued);                         // < 64 left
+            nqueued = 0u;
+        }
+        sink.end();
+        return;
+    }
+
+    // ---- row-by-row path -------------------------------------------------------------------
     for (uint32_t qbase = qs0; qbase < qs1; qbase += T) {
         const uint32_t qslot = qbase + tid;
         const bool active = qslot < qs1;
