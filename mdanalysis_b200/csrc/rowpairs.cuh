@@ -29,7 +29,9 @@ namespace mdagpu {
 constexpr int RP_TILE = 1024;             // staged candidates per buffer (row-by-row path)
 constexpr int RP_ALL = 3584;              // staged candidates of ALL rows (plane path): 3 x 14 kB
 constexpr int RP_QUEUE = 96;              // queued survivors per warp (drained at >= 32)
-constexpr size_t RP_DYN_BYTES = 3 * (RP_ALL + 4) * sizeof(float);   // >= 2 * RP_TILE * sizeof(float4)
+constexpr int RP_NQ = 1;                  // quads of candidates per trip of the plane path (2: spills, 3.2 -> 3.5 ms)
+constexpr int RP_PAD = 4 * RP_NQ;         // sentinels behind the last row (a trip may read past the end)
+constexpr size_t RP_DYN_BYTES = 3 * (RP_ALL + RP_PAD) * sizeof(float);   // >= 2 * RP_TILE * sizeof(float4)
 static_assert(RP_DYN_BYTES >= 2 * RP_TILE * sizeof(float4), "the row-by-row buffers live in the same allocation");
 
 template <int MIC, bool SELF, class Sink>
@@ -112,7 +114,7 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
     }
     __syncthreads();
     if (s_rowbase[nrows] <= (uint32_t)RP_ALL) {
-        float *px = reinterpret_cast<float *>(rp_dyn), *py = px + (RP_ALL + 4), *pz = py + (RP_ALL + 4);
+        float *px = reinterpret_cast<float *>(rp_dyn), *py = px + (RP_ALL + RP_PAD), *pz = py + (RP_ALL + RP_PAD);
         for (int r = 0; r < nrows; ++r) {
             const RowInfo &ri = bk.row[r];
             const uint32_t rb = s_rowbase[r];
@@ -122,7 +124,7 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                 px[rb + t] = c.x; py[rb + t] = c.y; pz[rb + t] = c.z;
             }
         }
-        if (tid < 4) {                                              // the last quad may read past the end
+        if (tid < RP_PAD) {                                         // the last trip may read past the end
             const uint32_t e = s_rowbase[nrows] + tid;
             px[e] = py[e] = pz[e] = 1.0e18f;
         }
@@ -202,24 +204,31 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                         // the lane's own part of this run as (first, width) for one unsigned compare
                         const uint32_t lo2 = max(lo, a), hi2 = min(hi, e);
                         const uint32_t width = hi2 > lo2 ? hi2 - lo2 : 0u;
-                        for (uint32_t qd = (rb + a) & ~3u; qd < rb + e; qd += 4u) {
-                            const float4 X = *reinterpret_cast<const float4 *>(px + qd);
-                            const float4 Y = *reinterpret_cast<const float4 *>(py + qd);
-                            const float4 Z = *reinterpret_cast<const float4 *>(pz + qd);
-                            const uint32_t rel = qd - rb - lo2;     // row coordinate of candidate 0, minus lo2 (mod 2^32)
-                            const float cxs[4] = { X.x, X.y, X.z, X.w }, cys[4] = { Y.x, Y.y, Y.z, Y.w }, czs[4] = { Z.x, Z.y, Z.z, Z.w };
-                            uint32_t m[4];
-                            bool keep[4];
+                        for (uint32_t qd = (rb + a) & ~3u; qd < rb + e; qd += 4u * RP_NQ) {
+                            float cxs[4 * RP_NQ], cys[4 * RP_NQ], czs[4 * RP_NQ];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
+                            for (int g = 0; g < RP_NQ; ++g) {
+                                const float4 X = *reinterpret_cast<const float4 *>(px + qd + 4 * g);
+                                const float4 Y = *reinterpret_cast<const float4 *>(py + qd + 4 * g);
+                                const float4 Z = *reinterpret_cast<const float4 *>(pz + qd + 4 * g);
+                                cxs[4 * g] = X.x; cxs[4 * g + 1] = X.y; cxs[4 * g + 2] = X.z; cxs[4 * g + 3] = X.w;
+                                cys[4 * g] = Y.x; cys[4 * g + 1] = Y.y; cys[4 * g + 2] = Y.z; cys[4 * g + 3] = Y.w;
+                                czs[4 * g] = Z.x; czs[4 * g + 1] = Z.y; czs[4 * g + 2] = Z.z; czs[4 * g + 3] = Z.w;
+                            }
+                            const uint32_t rel = qd - rb - lo2;     // row coordinate of candidate 0, minus lo2 (mod 2^32)
+                            uint32_t m[4 * RP_NQ], many = 0u;
+                            bool keep[4 * RP_NQ];
+#pragma unroll
+                            for (int k = 0; k < 4 * RP_NQ; ++k) {
                                 const float tx = qx - cxs[k], ty = qy - cys[k], tz = qz - czs[k];
                                 const float d2f = fmaf(tx, tx, fmaf(ty, ty, tz * tz));
                                 keep[k] = d2f <= sp.d2_filter && rel + (uint32_t)k < width;
                                 m[k] = __ballot_sync(0xffffffffu, keep[k]);
+                                many |= m[k];
                             }
-                            if (m[0] | m[1] | m[2] | m[3]) {
+                            if (many) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
+                                for (int k = 0; k < 4 * RP_NQ; ++k) {
                                     if (m[k] == 0u) continue;
                                     if (keep[k]) {
                                         const uint32_t at = nqueued + __popc(m[k] & ((1u << lane) - 1u));
