@@ -79,9 +79,13 @@ pair_rmsd_centre_kernel(const float *__restrict__ traj, uint64_t natoms, const i
 // runs of global memory) and, with rows of PR_LD doubles, its 8-byte shared stores are
 // conflict-free per half warp.  The values of the NEXT chunk are fetched into registers before
 // the current chunk is computed, so the global-load latency is covered by the arithmetic.
-constexpr int PR_SLOTS = PR_T * PR_KA * 3 / PR_THREADS;   // 6 per operand and thread
-
+// TF frames per tile side, KC coordinates per chunk, LD shared row pitch in doubles.
+template <int TF, int KC, int LD>
 struct PairStager {
+    static constexpr int NG = TF / 8;                    // warps side by side along the frames
+    static constexpr int STEP = 4 * (PR_THREADS / 32 / NG);   // coordinates covered per step of the CTA
+    static constexpr int SLOTS = KC / STEP;
+    static_assert(KC % STEP == 0 && TF % 8 == 0, "tile shape");
     const float *row;       // first coordinate of the thread's frame (nullptr: frame outside the trajectory)
     int fr, kc0;
     const double *c;        // centroid of the frame (superposition flavour), read when needed
@@ -89,32 +93,32 @@ struct PairStager {
                                          const FrameCentre *centres)
     {
         const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        fr = (w & 3) * 8 + (lane & 7);
-        kc0 = (w >> 2) * 4 + (lane >> 3);
+        fr = (w % NG) * 8 + (lane & 7);
+        kc0 = (w / NG) * 4 + (lane >> 3);
         const uint64_t f = f0 + fr;
         row = f < nframes ? traj + f * natoms * 3 : nullptr;
         c = (centres && row) ? centres[f].c : nullptr;
     }
-    // raw float32 values of chunk k0 (0 outside the selection / trajectory)
-    __device__ __forceinline__ void fetch(float (&v)[PR_SLOTS], const int32_t *__restrict__ sel, uint64_t nsel,
+    // raw float32 values of chunk k0 (0 outside the selection / trajectory); k0 counts atoms
+    __device__ __forceinline__ void fetch(float (&v)[SLOTS], const int32_t *__restrict__ sel, uint64_t nsel,
                                           uint64_t k0) const
     {
 #pragma unroll
-        for (int r = 0; r < PR_SLOTS; ++r) {
-            const int kc = kc0 + 8 * r;
+        for (int r = 0; r < SLOTS; ++r) {
+            const int kc = kc0 + STEP * r;
             const uint64_t k = k0 + kc / 3;
             v[r] = 0.0f;
             if (row && k < nsel) v[r] = sel ? row[(uint64_t)sel[k] * 3 + kc % 3] : row[k0 * 3 + kc];
         }
     }
-    // s[(atom * 3 + comp) * PR_LD + frame] = sqrt(w) * (x - centre)
+    // s[(atom * 3 + comp) * LD + frame] = sqrt(w) * (x - centre)
     template <bool FIT>
-    __device__ __forceinline__ void store(double *s, const float (&v)[PR_SLOTS], const double *__restrict__ sqw,
+    __device__ __forceinline__ void store(double *s, const float (&v)[SLOTS], const double *__restrict__ sqw,
                                           uint64_t nsel, uint64_t k0) const
     {
 #pragma unroll
-        for (int r = 0; r < PR_SLOTS; ++r) {
-            const int kc = kc0 + 8 * r;
+        for (int r = 0; r < SLOTS; ++r) {
+            const int kc = kc0 + STEP * r;
             const uint64_t k = k0 + kc / 3;
             double x = 0.0;
             if (row && k < nsel) {
@@ -122,10 +126,12 @@ struct PairStager {
                 if (FIT) x -= c[kc % 3];
                 if (sqw) x *= sqw[k];
             }
-            s[kc * PR_LD + fr] = x;
+            s[kc * LD + fr] = x;
         }
     }
 };
+using Stager32 = PairStager<PR_T, PR_KA * 3, PR_LD>;
+constexpr int PR_SLOTS = Stager32::SLOTS;
 
 template <bool FIT>
 __global__ void __launch_bounds__(PR_THREADS, FIT ? 2 : 3)
@@ -152,7 +158,7 @@ pair_rmsd_kernel(const float *__restrict__ traj, uint64_t nframes, uint64_t nato
 #pragma unroll
         for (int q = 0; q < NACC; ++q) acc[p][q] = 0.0;
 
-    PairStager sta, stb;
+    Stager32 sta, stb;
     sta.init(traj, nframes, natoms, i0, FIT ? centres : nullptr);
     stb.init(traj, nframes, natoms, j0, FIT ? centres : nullptr);
     // the nine-accumulator flavour has no registers to spare: it fetches just before it stores
@@ -237,6 +243,86 @@ pair_rmsd_kernel(const float *__restrict__ traj, uint64_t nframes, uint64_t nato
     }
 }
 
+// The plain metric on 64 x 64 tiles, a thread owning 4 x 4 pairs.  With 2 x 2 pairs the kernel above
+// is bound by the shared-memory instruction queue (ncu: mio_throttle 3.9, FP64 pipe 48 %): two LDS.128
+// feed eight FP64 instructions.  Here four LDS.128 feed thirty-two.
+constexpr int PR_T2 = 64;          // frames per tile side
+constexpr int PR_KA2 = 8;          // atoms per staged chunk
+constexpr int PR_LD2 = PR_T2 + 8;  // pitch: 144 words = 16 mod 32, conflict-free 8-byte stores per half warp
+using Stager64 = PairStager<PR_T2, PR_KA2 * 3, PR_LD2>;
+
+__global__ void __launch_bounds__(PR_THREADS, 2)
+pair_rmsd_plain_kernel(const float *__restrict__ traj, uint64_t nframes, uint64_t natoms,
+                       const int32_t *__restrict__ sel, uint64_t nsel, const double *__restrict__ sqw,
+                       double cutoff, double *__restrict__ out)
+{
+    const unsigned nt = (unsigned)((nframes + PR_T2 - 1) / PR_T2);
+    unsigned ti = 0, rest = blockIdx.x;
+    while (rest >= nt - ti) { rest -= nt - ti; ++ti; }
+    const unsigned tj = ti + rest;
+    const uint64_t i0 = (uint64_t)ti * PR_T2, j0 = (uint64_t)tj * PR_T2;
+    const bool offdiag = tj != ti;
+
+    __shared__ __align__(16) double sa[PR_KA2 * 3 * PR_LD2];
+    __shared__ __align__(16) double sb[PR_KA2 * 3 * PR_LD2];
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;   // rows 4ty..4ty+3; columns 2tx, 2tx+1, 32+2tx, 33+2tx
+
+    double acc[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+
+    Stager64 sta, stb;
+    sta.init(traj, nframes, natoms, i0, nullptr);
+    stb.init(traj, nframes, natoms, j0, nullptr);
+    float va[Stager64::SLOTS], vb[Stager64::SLOTS];
+    sta.fetch(va, sel, nsel, 0);
+    if (offdiag) stb.fetch(vb, sel, nsel, 0);
+    const double *pa = sa + 4 * ty;
+    const double *pb = (offdiag ? sb : sa) + 2 * tx;
+
+    for (uint64_t k0 = 0; k0 < nsel; k0 += PR_KA2) {
+        __syncthreads();                       // the previous chunk has been consumed
+        sta.store<false>(sa, va, sqw, nsel, k0);
+        if (offdiag) stb.store<false>(sb, vb, sqw, nsel, k0);
+        __syncthreads();
+        if (k0 + PR_KA2 < nsel) {              // in flight while this chunk is computed
+            sta.fetch(va, sel, nsel, k0 + PR_KA2);
+            if (offdiag) stb.fetch(vb, sel, nsel, k0 + PR_KA2);
+        }
+#pragma unroll 4
+        for (int kc = 0; kc < PR_KA2 * 3; ++kc) {
+            const double2 a01 = *reinterpret_cast<const double2 *>(pa + kc * PR_LD2);
+            const double2 a23 = *reinterpret_cast<const double2 *>(pa + kc * PR_LD2 + 2);
+            const double2 b01 = *reinterpret_cast<const double2 *>(pb + kc * PR_LD2);
+            const double2 b23 = *reinterpret_cast<const double2 *>(pb + kc * PR_LD2 + 32);
+            const double av[4] = { a01.x, a01.y, a23.x, a23.y }, bv[4] = { b01.x, b01.y, b23.x, b23.y };
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double d = av[p] - bv[q];
+                    acc[p][q] = fma(d, d, acc[p][q]);
+                }
+        }
+    }
+
+    const double n = (double)nsel;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint64_t i = i0 + 4 * ty + p, j = j0 + 2 * tx + (q & 1) + 32 * (q >> 1);
+            if (i >= nframes || j >= nframes) continue;
+            if (!offdiag && j < i) continue;   // the lower triangle of a diagonal tile is filled from the upper
+            double r = sqrt(acc[p][q] / n);
+            r = r > cutoff ? r : 0.0;          // diffusionmap.py:262-263
+            out[i * nframes + j] = r;
+            out[j * nframes + i] = r;          // diffusionmap.py:264-267
+        }
+}
+
 }  // namespace mdagpu
 
 using namespace mdagpu;
@@ -289,15 +375,17 @@ extern "C" int mdagpu_pairwise_rmsd(const float *traj, uint64_t nframes, uint64_
                    w_dev, centres.as<FrameCentre>());
         MDA_CHECK_LAUNCH();
     }
-    const unsigned grid = (unsigned)(nt * (nt + 1) / 2);
-    if (superposition)
+    if (superposition) {
+        const unsigned grid = (unsigned)(nt * (nt + 1) / 2);
         MDA_LAUNCH_AS("pair_rmsd_kernel", pair_rmsd_kernel<true>, grid, PR_THREADS, 0, st, t.as<float>(), nframes, natoms,
                       s.as<int32_t>(), nsel, weights ? sqw.as<double>() : nullptr, centres.as<FrameCentre>(), cutoff,
                       o.as<double>());
-    else
-        MDA_LAUNCH_AS("pair_rmsd_kernel", pair_rmsd_kernel<false>, grid, PR_THREADS, 0, st, t.as<float>(), nframes, natoms,
-                      s.as<int32_t>(), nsel, weights ? sqw.as<double>() : nullptr, (const FrameCentre *)nullptr, cutoff,
+    } else {
+        const uint64_t nt2 = (nframes + PR_T2 - 1) / PR_T2;
+        MDA_LAUNCH_AS("pair_rmsd_kernel", pair_rmsd_plain_kernel, (unsigned)(nt2 * (nt2 + 1) / 2), PR_THREADS, 0, st,
+                      t.as<float>(), nframes, natoms, s.as<int32_t>(), nsel, weights ? sqw.as<double>() : nullptr, cutoff,
                       o.as<double>());
+    }
     MDA_CHECK_LAUNCH();
     MDA_CUDA(o.finish());
     MDA_CUDA(cudaStreamSynchronize(st));   // host-side weight buffers are sources of async copies
