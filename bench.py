@@ -224,7 +224,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------
@@ -508,13 +508,33 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clock_info, "parity_device_vs_host_path": same, "secondary": secondary,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist_ready:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line.  Libraries below (NCCL's version banner, anything a C
+    extension prints) write to file descriptor 1 directly, so fd 1 is pointed at stderr for the
+    rest of the process and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
