@@ -40,7 +40,9 @@ if [ -d "$TS" ]; then
            analysis/YiiP_lipids.gro.gz martini_dppc_chol_bilayer.gro adk_oplsaa.pdb A6PA6_alpha.pdb cobrotoxin.pdb adk.psf \
            surface.pdb.bz2 surface.trr adk_oplsaa.tpr adk_oplsaa.xtc analysis/YiiP_lipids.xtc contacts/2F4K_qlist5_remap.dat \
            contacts/villin_folded.gro.bz2 contacts/villin_unfolded.gro.bz2 adk_oplsaa_CA_rmsf.npy two_water_gro.gro \
-           tip125_tric_C36.psf tip125_tric_C36.dcd dppc_vesicle_hg.gro adk_open.pdb; do
+           tip125_tric_C36.psf tip125_tric_C36.dcd dppc_vesicle_hg.gro adk_open.pdb trz_psf.psf trzfile.trz 1osm.pdb.gz \
+           watdyn.psf watdyn.dcd namd_cgenff.psf namd_cgenff.pdb lammps/a_lot_of_bond_types.data 19hc.pdb.gz 1a28.pdb.gz adk_oplsaa_GLY_rama.npy \
+           adk_oplsaa_LYS_janin.npy adk_oplsaa_dihedral.npy adk_oplsaa_dihedral_list.npy adk_oplsaa_janin.npy adk_oplsaa_rama.npy; do
     mkdir -p "$HERE/_ref/MDAnalysisTests/data/$(dirname "$f")"
     cp "$TS/data/$f" "$HERE/_ref/MDAnalysisTests/data/$f"
   done

@@ -18,7 +18,7 @@ from __future__ import annotations
 
 
 def install(patch_capped: bool = False, masquerade=None, capped_default: str = "serial",
-            patch_classes: bool = False):
+            patch_classes: bool = False, patch_analysis: bool = False):
     """Register ``backend='cuda'`` with MDAnalysis.  Returns the patched module.
 
     masquerade      also install the module under existing key(s) (``'serial'``, or a list like
@@ -28,6 +28,9 @@ def install(patch_capped: bool = False, masquerade=None, capped_default: str = "
     patch_classes   also point ``MDAnalysis.lib.nsgrid.FastNS`` and
                     ``MDAnalysis.lib.qcprot.CalcRMSDRotationalMatrix`` at the GPU twins (what the
                     reference's ``test_nsgrid.py`` / ``test_qcprot.py`` / ``analysis.rms`` call).
+    patch_analysis  ``analysis.diffusionmap.DistanceMatrix.run`` computes the matrix with
+                    ``run_on_gpu`` when the metric is ``rms.rmsd`` (the override INTEGRATION.md 3b
+                    shows); other metrics keep the reference's Python loop.
     """
     import MDAnalysis.lib.distances as mda_distances
 
@@ -44,6 +47,21 @@ def install(patch_capped: bool = False, masquerade=None, capped_default: str = "
         from .lib import qcprot as gpu_qcprot
         mda_nsgrid.FastNS = gpu_nsgrid.FastNS
         mda_qcprot.CalcRMSDRotationalMatrix = gpu_qcprot.CalcRMSDRotationalMatrix
+    if patch_analysis:
+        import MDAnalysis.analysis.diffusionmap as mda_dmap
+        from .adapters import run_on_gpu
+        from .analysis.diffusionmap import _metric_kind
+        ref_run = mda_dmap.DistanceMatrix.run
+        if not getattr(ref_run, "_mdagpu", False):
+            def run(self, start=None, stop=None, step=None, frames=None, verbose=None, **kwargs):
+                try:
+                    _metric_kind(self._metric)
+                except NotImplementedError:
+                    return ref_run(self, start=start, stop=stop, step=step, frames=frames, verbose=verbose, **kwargs)
+                return run_on_gpu(self, start=start, stop=stop, step=step, frames=frames)
+            run._mdagpu = True
+            run.__doc__ = ref_run.__doc__
+            mda_dmap.DistanceMatrix.run = run
     if patch_capped:
         ref_capped = mda_distances.capped_distance
         ref_self_capped = mda_distances.self_capped_distance

@@ -19,7 +19,8 @@ def pytest_configure(config):
     import warnings
     warnings.filterwarnings("ignore")
     import mdanalysis_b200.register as reg
-    reg.install(patch_capped=True, masquerade=["serial", "openmp"], capped_default="cuda", patch_classes=True)
+    reg.install(patch_capped=True, masquerade=["serial", "openmp"], capped_default="cuda", patch_classes=True,
+                patch_analysis=True)
     from mdanalysis_b200 import _cabi
     config._mdagpu_launches0 = _cabi.launch_count()
 
