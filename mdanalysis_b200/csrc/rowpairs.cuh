@@ -45,6 +45,7 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
     extern __shared__ __align__(16) unsigned char rp_dyn[];         // RP_DYN_BYTES
     float4 (*tile)[RP_TILE] = reinterpret_cast<float4 (*)[RP_TILE]>(rp_dyn);
     __shared__ uint32_t s_rowbase[ROW_MAXROWS + 1];
+    __shared__ uint32_t s_next;                                     // next unclaimed work item (plane path)
     __shared__ uint32_t s_qq[NW][RP_QUEUE], s_qc[NW][RP_QUEUE];
     __shared__ uint8_t s_qi[NW][RP_QUEUE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -128,9 +129,19 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
             const uint32_t e = s_rowbase[nrows] + tid;
             px[e] = py[e] = pz[e] = 1.0e18f;
         }
+        if (tid == 0) s_next = (uint32_t)NW;
         __syncthreads();
-        for (uint32_t qbase = qs0; qbase < qs1; qbase += T) {
-            const uint32_t qslot = qbase + tid;
+        // Work items = (chunk of 32 queries, part of the rows), part-major; warp w starts with item w and
+        // claims the next unclaimed one when it is done.  A home cell of ~82 queries is three chunks: with
+        // one static chunk per warp the fourth warp of the CTA had nothing to do and the 51 kB of the CTA
+        // stayed allocated until the slowest warp was through all 14 rows.
+        const int nchunk = (int)((qs1 - qs0 + 31u) >> 5);
+        const int nparts = nrows >= 4 ? 2 : 1;
+        const int nitems = nchunk * nparts;
+        for (int item = warp; item < nitems;) {
+            const int part = item / nchunk, chunk = item - part * nchunk;
+            const int ra = nrows * part / nparts, rb = nrows * (part + 1) / nparts;
+            const uint32_t qslot = qs0 + 32u * (uint32_t)chunk + lane;
             const bool active = qslot < qs1;
             float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
             int cxl = 0;
@@ -138,13 +149,12 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                 q = q_atoms[qslot];
                 while (cxl + 1 < nh && bk.qst[cxl + 1] <= qslot) ++cxl;
             }
-            if (SELF && sp.include_self && active) {
+            if (SELF && sp.include_self && active && ra == 0) {
                 const double d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, q.x, q.y, q.z, box);
                 if (d2 <= sp.d2_max && d2 > sp.d2_min) sink.template hit_w<false>(__float_as_int(q.w), __float_as_int(q.w), d2, f);
             }
             const int cmin = (int)__reduce_min_sync(0xffffffffu, active ? (unsigned)cxl : 0x7fffffffu);
             const int cmax = (int)__reduce_max_sync(0xffffffffu, active ? (unsigned)cxl : 0u);
-            if (cmin == 0x7fffffff) continue;                       // no query in this warp (uniform)
             // float64 evaluation of up to 64 queued survivors, two per lane: the queue names the lane
             // that owns the query (a shuffle instead of a gather), both candidates are fetched before
             // either is used, and the accepted pairs of both rounds share one atomic
@@ -174,7 +184,7 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                           v1 && d1 <= sp.d2_max && d1 > sp.d2_min, __float_as_int(q1.w), __float_as_int(c1.w), d1);
                 __syncwarp();
             };
-            for (int r = 0; r < nrows; ++r) {
+            for (int r = ra; r < rb; ++r) {
                 const RowInfo &ri = bk.row[r];
                 if (ri.end[2] == 0u) continue;
                 const bool home = SELF && r == 0;
@@ -250,6 +260,9 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
             }
             if (nqueued) drain(0u, nqueued);                         // < 64 left
             nqueued = 0u;
+            uint32_t nxt = 0;
+            if (lane == 0) nxt = atomicAdd(&s_next, 1u);
+            item = (int)__shfl_sync(0xffffffffu, nxt, 0);
         }
         sink.end();
         return;
