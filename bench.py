@@ -404,6 +404,19 @@ def secondary_benchmarks(torch, hbm_peak, peak_kind, quick):
         ms = timed(lambda: self_contacts(cpos, 8.0, box=bx), 2)
         pairs = Fc * (nc * (nc - 1) // 2)
         out[f"contacts_self_{name}"] = {"atoms": nc, "frames": Fc, "ms": ms, "pair_decisions_per_s": pairs / ms * 1e3}
+    # C5 (i): the materialised self_distance_array of one 100k-atom frame (40 GB of float64, written once)
+    npair = nc * (nc - 1) // 2
+    big = torch.empty((npair,), dtype=torch.float64, device=dev)
+    one = cpos[:1].contiguous()
+    for name, (mode, b) in (("none", (0, None)), ("ortho", (1, np.array([side] * 3, dtype=np.float32)))):
+        ms = timed(lambda: _cabi.check(lib.mdagpu_self_distance_array(
+            _cabi.tensor_ptr(one), nc, mode, _cabi.ptr(b), _cabi.tensor_ptr(big), 1, 1, _cabi.current_stream(one))), 2)
+        gbs = npair * 8 / ms / 1e6
+        out[f"c5_self_distance_array_{name}"] = {"atoms": nc, "pairs": npair, "ms": ms, "pairs_per_s": npair / ms * 1e3,
+                                                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                                              "frac": gbs / hbm_peak, "peak_kind": peak_kind}}
+    del big
+    torch.cuda.empty_cache()
     return out
 
 
