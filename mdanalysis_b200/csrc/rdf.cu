@@ -13,7 +13,7 @@
 // conversion-unit instruction: floor() is a magic-number add (the XU pipe runs at
 // 16 lanes/clk/SM on B200, profiles/microbench/pipes_b200.txt, and is kept for
 // the one MUFU.RSQ per step).
-#include "rowquad.cuh"
+#include "rowfine.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -42,6 +42,29 @@ void grid_geometry_ortho_free(double cutoff, const float *L3, const double *orig
         } else {
             g->periodic[k] = 0;
         }
+        g->ncells[k] = n;
+        g->cs[4 * k] = (double)L3[k] / (double)n;
+        total *= n;
+    }
+    g->ncell_total = total;
+}
+
+// Orthorhombic grid with a different minimum cell width per axis (rowfine.cuh: fine cells
+// along x, cutoff / 2 along y and z).
+static void grid_geometry_ortho_axes(const double *cutoff3, const float *L3, GridGeom *g)
+{
+    g->triclinic = 0;
+    g->pbc = 1;
+    for (int k = 0; k < 9; ++k) g->cs[k] = 0.0;
+    int64_t total = 1;
+    for (int k = 0; k < 3; ++k) {
+        const double cs_min = cutoff3[k] * (1.0 + 1e-4) + 1e-3;
+        g->origin[k] = 0.0;
+        double nc = floor((double)L3[k] / cs_min);
+        if (!(nc >= 1.0)) nc = 1.0;
+        if (nc > 256.0) nc = 256.0;
+        const int n = (int)nc;
+        g->periodic[k] = n >= 3 ? 1 : 0;
         g->ncells[k] = n;
         g->cs[4 * k] = (double)L3[k] / (double)n;
         total *= n;
@@ -150,6 +173,53 @@ struct HistSink {
 #pragma unroll
             for (int w = 0; w < T / 32; ++w) sum += s_hist[w * nbins + k];
             if (sum) atomicAdd(&counts[k], sum);
+        }
+    }
+};
+
+// Histogram of rowfine.cuh: ONE histogram per CTA, bin-major with 1 << ls_shift lane columns
+// per bin (word = (bin << ls_shift) + (lane & mask)); with 32 columns every warp-wide RED is
+// conflict free.  Two scratch rows (nbins, nbins + 1) take the misses.
+template <int T>
+struct HistSinkFine {
+    static constexpr int THREADS = T;
+    static constexpr bool FAST = true;
+    const double *thr;            // [nbins+1] exact thresholds on d2 (device)
+    unsigned long long *counts;   // [nbins] global histogram
+    int nbins, ls_shift;
+    float c0, inv_dr, band_lim;
+
+    __device__ __forceinline__ int hist_words() const { return (nbins + 2) << ls_shift; }
+    __device__ __forceinline__ uint32_t hist_addr() const
+    {
+        extern __shared__ uint32_t s_hist[];
+        return (uint32_t)__cvta_generic_to_shared(s_hist);
+    }
+    __device__ __forceinline__ void begin()
+    {
+        extern __shared__ uint32_t s_hist[];
+        for (int w = threadIdx.x; w < hist_words(); w += T) s_hist[w] = 0u;
+    }
+    template <bool SYM> __device__ __forceinline__ void hit_w(int i, int j, double d2, uint64_t)
+    {
+        extern __shared__ uint32_t s_hist[];
+        const uint32_t wgt = (SYM && i != j) ? 2u : 1u;
+        if (!(d2 >= thr[0]) || !(d2 <= thr[nbins])) return;     // np.histogram keeps lo <= d <= hi
+        int k = (int)(fmaf(sqrtf((float)d2), inv_dr, c0) + 0.5f);
+        k = k < 0 ? 0 : (k > nbins - 1 ? nbins - 1 : k);
+        while (k > 0 && d2 < thr[k]) --k;
+        while (k < nbins - 1 && d2 >= thr[k + 1]) ++k;
+        atomicAdd(s_hist + (k << ls_shift) + (threadIdx.x & ((1 << ls_shift) - 1)), wgt);
+    }
+    __device__ __forceinline__ void end()
+    {
+        extern __shared__ uint32_t s_hist[];
+        __syncthreads();
+        const int cols = 1 << ls_shift;
+        for (int k = threadIdx.x; k < nbins; k += T) {
+            uint32_t sum = 0;                                  // wraps like the columns do (transient un-counts)
+            for (int c = 0; c < cols; ++c) sum += s_hist[(k << ls_shift) + ((c + threadIdx.x) & (cols - 1))];
+            if (sum) atomicAdd(&counts[k], (unsigned long long)sum);
         }
     }
 };
@@ -414,7 +484,8 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
                                double d2_max, int use_grid, const double *thresholds,
                                int nbins, double r_lo, double r_hi, int excl_a, int excl_b,
                                const int32_t *ids_a_host, const int32_t *ids_b_host,
-                               unsigned long long *counts, int per_site, int space, mdagpu_stream_t stream)
+                               unsigned long long *counts, int per_site, int space, mdagpu_stream_t stream,
+                               int force_basic = 0)
 {
     cudaStream_t st = (cudaStream_t)stream;
     MDA_REQUIRE(A && thresholds && counts, "mdagpu_rdf_accumulate: NULL argument");
@@ -437,7 +508,58 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     const uint64_t nbox = boxes_per_frame ? nframes : 1;
     std::vector<FrameGeom> fgs(nbox);
     int W = 0;                                  // 0: cell_tile_kernel on the reference grid
-    const int tiled = !use_grid ? 0 : (mic == MIC_ORTHO_LAZY ? 2 : (mic == MIC_TRICLINIC ? 1 : 0));
+    const int tiled = (!use_grid || force_basic == 1) ? 0 : (mic == MIC_ORTHO_LAZY ? 2 : (mic == MIC_TRICLINIC ? 1 : 0));
+    // the packed kernels (rowfine.cuh, rowquad.cuh) fold the cutoff into the top histogram edge and
+    // have no exclusion blocks
+    const bool by_ids = ids_a_host != nullptr;
+    const bool packed_ok = tiled == 2 && !per_site && !by_ids && excl_a == 0 && r_hi > 0.0 && r_lo <= 0.0
+                           && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max && !getenv("MDAGPU_RDF_NO_QUAD");
+    // ---- rowfine.cuh: fine cells along x (cutoff / WX), cutoff / 2 along y and z ----
+    int fineWX = 0;
+    float fine_reach = 0.0f;
+    if (packed_ok && force_basic != 2 && !getenv("MDAGPU_RDF_NO_FINE")) {
+        const int choices[2] = { 8, 4 };
+        for (int ci = 0; ci < 2 && !fineWX; ++ci) {
+            const int wx = choices[ci];
+            bool ok = true;
+            int64_t base = 0;
+            double reach = 0.0;
+            for (uint64_t f = 0; f < nbox && ok; ++f) {
+                FrameGeom &fg = fgs[f];
+                const float *b6 = box6 + 6 * f;
+                fg.box = make_box_params(BOX_ORTHO, b6);
+                float mc = 0.0f;
+                grid_geometry_reference(cutoff, b6, h9 + 9 * f, 1, &fg.grid, &mc);
+                MDA_REQUIRE(!(cutoff > (double)mc), "Cutoff %g too large for box (max %g)", cutoff, (double)mc);
+                const double c3[3] = { cutoff / wx, cutoff / 2.0, cutoff / 2.0 };
+                grid_geometry_ortho_axes(c3, b6, &fg.grid);
+                const GridGeom &g = fg.grid;
+                const double lmax = fmax((double)b6[0], fmax((double)b6[1], (double)b6[2]));
+                // margin of the per-lane windows: FP32 evaluation of the gaps (box-sized values)
+                const double rch = cutoff * (1.0 + 2e-5) + 1e-4 + 4e-6 * lmax;
+                reach = fmax(reach, rch);
+                const int w3[3] = { wx, 2, 2 };
+                for (int k = 0; k < 3; ++k) {
+                    if (!g.periodic[k] || g.ncells[k] < 2 * w3[k] + 2) ok = false;
+                    if (!(rch <= w3[k] * g.cs[4 * k])) ok = false;                 // the stencil covers the reach
+                    if (!((double)b6[k] > 2.0 * rch + 2.0 * g.cs[4 * k])) ok = false;   // one image per window
+                }
+                // the FP32 path needs a usable band (see derive() below) and a histogram that fits
+                {
+                    const double inv = (double)nbins / (r_hi - r_lo);
+                    const double u_err = (4e-7 * fmax(fabs(r_hi), fabs(r_lo)) + rowquad_abs_err(fg.box, cutoff)) * inv
+                                         + 2e-7 * (fabs(-r_lo * inv - 0.5) + (double)nbins);
+                    if (!(fmax(5e-4, 2.0 * u_err) < 0.2)) ok = false;
+                    if ((size_t)(nbins + 2) * sizeof(uint32_t) > 20 * 1024) ok = false;
+                }
+                // thin cells make the staged rows mostly bookkeeping
+                if ((double)nb / (double)g.ncell_total < (wx == 8 ? 1.5 : 0.75)) ok = false;
+                fg.cell_base = base;
+                base += g.ncell_total;
+            }
+            if (ok) { fineWX = wx; fine_reach = (float)reach; W = 2; }
+        }
+    }
     for (int tryW = tiled; tryW >= 0 && W == 0; --tryW) {
         int64_t base = 0;
         bool ok = tryW > 0;
@@ -469,12 +591,8 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
         if (ok) W = tryW;
     }
     const int64_t cells_per_frame = boxes_per_frame ? 0 : fgs[0].grid.ncell_total;
-    // the packed kernel (rowquad.cuh) folds the cutoff into the top histogram edge, has no
-    // exclusion blocks and keeps one 32-bit histogram per warp of a 128-thread CTA
-    const bool by_ids = ids_a_host != nullptr;
-    const bool quad = !per_site && !by_ids && W > 0 && mic == MIC_ORTHO_LAZY && r_hi > 0.0 && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max
-                      && excl_a == 0 && (size_t)nbins * 4 * sizeof(uint32_t) <= 160 * 1024
-                      && !getenv("MDAGPU_RDF_NO_QUAD");
+    // rowquad.cuh keeps one 32-bit histogram per warp of a 128-thread CTA
+    const bool quad = packed_ok && W > 0 && (size_t)nbins * 4 * sizeof(uint32_t) <= 160 * 1024;
     // error of the FP32 distance estimate for the row traversals (per-cell-pair image prediction)
     // and for the per-pair traversals the code falls back to (27-image FP32 scan for triclinic cells)
     double err_row = 0.0, err_cell = 0.0;
@@ -530,6 +648,13 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     const uint64_t max_atoms = 1ull << 27;                 // 128 Mi atoms (2 GiB of float4) per chunk
     if (chunk * per_frame_atoms > max_atoms) chunk = max_atoms / per_frame_atoms ? max_atoms / per_frame_atoms : 1;
     if (chunk > 65535) chunk = 65535;
+    if (fineWX) {
+        // the planner's record lists: ~11 kB per (y, z) row and x segment; at most 1 GiB per chunk
+        const uint64_t rows = (uint64_t)fgs[0].grid.ncells[1] * (uint64_t)fgs[0].grid.ncells[2];
+        uint64_t by_lists = (2ull << 30) / (rows * 4ull * 4096ull * 2ull);
+        if (by_lists < 1) by_lists = 1;
+        if (chunk > by_lists) chunk = by_lists;
+    }
     if (!boxes_per_frame && cells_per_frame > 0) {
         uint64_t by_cells = (uint64_t)((1ull << 30) / (uint64_t)cells_per_frame);
         if (by_cells < 1) by_cells = 1;
@@ -609,14 +734,133 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
         tv.row = W > 0;
         tv.quad = quad;
         tv.chunks = 1;
-        if (tv.row && mic == MIC_TRICLINIC) {
+        if (tv.row) {
             // an atom that the float64 cell arithmetic folded into a cell it does not lie
-            // in breaks the per-cell image prediction: take the per-pair kernel instead
+            // in (a coordinate the reference's wrap left ON the upper face of the cell, e.g.
+            // -1e-7 + L == L in float32) breaks the per-cell image prediction: the per-pair
+            // kernel takes over -- for orthorhombic cells on the reference's own grid
             unsigned bad[2] = { 0u, 0u };
             MDA_CUDA(cudaMemcpyAsync(&bad[0], cl.inconsistent(), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             if (!same) MDA_CUDA(cudaMemcpyAsync(&bad[1], ql.inconsistent(), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             MDA_CUDA(cudaStreamSynchronize(st));
-            if (bad[0] | bad[1]) tv.row = 0;
+            if (bad[0] | bad[1]) {
+                if (mic == MIC_TRICLINIC) tv.row = 0;
+                else {
+                    rc = rdf_accumulate_impl(a_dev, na, same ? nullptr : b_dev, nb, fc, boxes_per_frame ? box6 + 6 * f0 : box6,
+                                             boxes_per_frame ? h9 + 9 * f0 : h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
+                                             use_grid, thresholds, nbins, r_lo, r_hi, excl_a, excl_b, ids_a_host, ids_b_host,
+                                             cnt.as<unsigned long long>(), per_site, MDAGPU_DEVICE, stream, 1);
+                    if (rc) return rc;
+                    if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
+                    continue;
+                }
+            }
+        }
+        if (fineWX && tv.row) {
+            // rowfine.cuh: a CTA owns R fine home cells of a (y, z) row (the whole row when its queries fit
+            // 224 threads and the staged rows fit the tile); a planner kernel writes row descriptors and
+            // sorted window records, the walker stages and bins.  Densities the two cannot take (tile,
+            // record list or thread count exceeded somewhere) go to rowquad.cuh on its own grid.
+            int nx_max = 0, rows_max = 0;
+            for (uint64_t f = boxes_per_frame ? f0 : 0; f < (boxes_per_frame ? f0 + fc : 1); ++f) {
+                const GridGeom &g = fgs[f].grid;
+                nx_max = g.ncells[0] > nx_max ? g.ncells[0] : nx_max;
+                rows_max = g.ncells[1] * g.ncells[2] > rows_max ? g.ncells[1] * g.ncells[2] : rows_max;
+            }
+            const double occ_q = (double)na * (double)fc / (double)total_cells;
+            const double occ_c = (double)nb * (double)fc / (double)total_cells;
+            const int nrows = same ? 13 : 25;
+            const int list_cap = same ? 2816 : 4096;
+            double q_target = 208.0;
+            if (0.85 * list_cap / nrows < q_target) q_target = 0.85 * list_cap / nrows;
+            int R = (int)(q_target / fmax(occ_q, 1e-9));
+            const int r_tile = (int)(0.9 * RF_CAP / (nrows * fmax(occ_c, 1e-9))) - 2 * fineWX;
+            if (R > r_tile) R = r_tile;
+            if (R > RF_MAXEXT - 2 * fineWX) R = RF_MAXEXT - 2 * fineWX;
+            if (R > nx_max) R = nx_max;
+            if (R < 1) R = 1;
+            const int runs = (nx_max + R - 1) / R;
+            R = (nx_max + runs - 1) / runs;              // even split of the row
+            FineParams fp;
+            fp.W = 2; fp.WX = fineWX; fp.R = R; fp.reach = fine_reach;
+            fp.debug = getenv("MDAGPU_FINE_DEBUG") ? atoi(getenv("MDAGPU_FINE_DEBUG")) : 0;
+            const Derived dv = derive(err_row);
+            SearchParams spc = sp;
+            spc.d2_filter = dv.d2_filter;
+            spc.include_self = report_self;
+            const uint64_t units_x = (uint64_t)runs * (uint64_t)rows_max, n_units = units_x * fc;
+            const size_t unit_bytes = same ? sizeof(FineUnit<13>) : sizeof(FineUnit<25>);
+            DevBuf units, lists, oflag;
+            MDA_CUDA(units.alloc(n_units * unit_bytes, st));
+            MDA_CUDA(lists.alloc(n_units * (size_t)list_cap * sizeof(uint32_t), st));
+            MDA_CUDA(oflag.alloc(sizeof(unsigned), st));
+            MDA_CUDA(cudaMemsetAsync(oflag.p, 0, sizeof(unsigned), st));
+            dim3 grid((unsigned)units_x, (unsigned)fc);
+            const size_t plan_smem = (size_t)nrows * (size_t)(R + 2 * fineWX + 1) * sizeof(uint32_t);
+            if (same)
+                MDA_LAUNCH_AS("rdf_window_planner", (fine_plan_kernel<true, 224>), grid, 224, plan_smem, st, cl.atoms(), cl.start(),
+                              cl.start(), fgd, boxes_per_frame, fgs[boxes_per_frame ? f0 : 0], fp, RF_CAP, list_cap,
+                              units.as<FineUnit<13>>(), lists.as<uint32_t>(), oflag.as<unsigned>());
+            else
+                MDA_LAUNCH_AS("rdf_window_planner", (fine_plan_kernel<false, 224>), grid, 224, plan_smem, st, ql.atoms(), ql.start(),
+                              cl.start(), fgd, boxes_per_frame, fgs[boxes_per_frame ? f0 : 0], fp, RF_CAP, list_cap,
+                              units.as<FineUnit<25>>(), lists.as<uint32_t>(), oflag.as<unsigned>());
+            MDA_CHECK_LAUNCH();
+            unsigned over = 0u;
+            MDA_CUDA(cudaMemcpyAsync(&over, oflag.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            MDA_CUDA(cudaStreamSynchronize(st));
+            if (over) {
+                rc = rdf_accumulate_impl(a_dev, na, same ? nullptr : b_dev, nb, fc, boxes_per_frame ? box6 + 6 * f0 : box6,
+                                         boxes_per_frame ? h9 + 9 * f0 : h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
+                                         use_grid, thresholds, nbins, r_lo, r_hi, excl_a, excl_b, ids_a_host, ids_b_host,
+                                         cnt.as<unsigned long long>(), per_site, MDAGPU_DEVICE, stream, 2);
+                if (rc) return rc;
+                if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
+                continue;
+            }
+            // lane columns of the histogram: 16 keep four CTAs on an SM (55 kB each)
+            int ls = 4;
+            while (ls > 0 && ((size_t)(nbins + 2) << ls) * sizeof(uint32_t) > 10 * 1024) --ls;
+            if (getenv("MDAGPU_RDF_LS")) ls = atoi(getenv("MDAGPU_RDF_LS"));
+            HistSinkFine<224> sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, ls, c0, inv_dr, dv.band_lim };
+            const size_t hist = ((((size_t)(nbins + 2) << ls) * sizeof(uint32_t)) + 15) & ~(size_t)15;
+            const size_t total = hist + 3 * (size_t)RF_CAP * sizeof(float);
+            {
+                static bool attr_set = false;
+                if (!attr_set) {
+                    MDA_CUDA(cudaFuncSetAttribute(fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    MDA_CUDA(cudaFuncSetAttribute(fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    attr_set = true;
+                }
+            }
+            const BoxParams bx = fgs[boxes_per_frame ? f0 : 0].box;
+            // (per-frame boxes: the walker only needs the box for the rare float64 evaluations; frames of
+            // one call that differ in their box are binned frame by frame)
+            if (boxes_per_frame) {
+                for (uint64_t ff = 0; ff < fc; ++ff) {
+                    dim3 g1((unsigned)units_x, 1u);
+                    const BoxParams bxf = fgs[f0 + ff].box;
+                    if (same)
+                        MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>), g1, 224, total, st,
+                                      cl.atoms(), cl.atoms(), units.as<FineUnit<13>>() + ff * units_x,
+                                      lists.as<uint32_t>() + ff * units_x * list_cap, list_cap, bxf, spc, sink);
+                    else
+                        MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>), g1, 224, total, st,
+                                      ql.atoms(), cl.atoms(), units.as<FineUnit<25>>() + ff * units_x,
+                                      lists.as<uint32_t>() + ff * units_x * list_cap, list_cap, bxf, spc, sink);
+                }
+            } else if (same) {
+                MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>), grid, 224, total, st,
+                              cl.atoms(), cl.atoms(), units.as<FineUnit<13>>(), lists.as<uint32_t>(), list_cap, bx, spc, sink);
+            } else {
+                MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>), grid, 224, total, st,
+                              ql.atoms(), cl.atoms(), units.as<FineUnit<25>>(), lists.as<uint32_t>(), list_cap, bx, spc, sink);
+            }
+            MDA_CHECK_LAUNCH();
+            if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
+            continue;
         }
         int threads;
         if (tv.row) {
@@ -829,3 +1073,4 @@ extern "C" int mdagpu_contacts_self(const float *xyz, uint64_t n, uint64_t nfram
     if (degree) MDA_CUDA(deg.finish());
     return MDAGPU_OK;
 }
+
