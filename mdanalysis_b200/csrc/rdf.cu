@@ -770,9 +770,9 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             const double occ_q = (double)na * (double)fc / (double)total_cells;
             const double occ_c = (double)nb * (double)fc / (double)total_cells;
             const int nrows = same ? 13 : 25;
-            const int list_cap = same ? 2816 : 4096;
+            const int list_cap = same ? 1664 : 3072;            // window records per unit (one per pair of queries and row)
             double q_target = 208.0;
-            if (0.85 * list_cap / nrows < q_target) q_target = 0.85 * list_cap / nrows;
+            if (1.7 * list_cap / nrows < q_target) q_target = 1.7 * list_cap / nrows;
             int R = (int)(q_target / fmax(occ_q, 1e-9));
             const int r_tile = (int)(0.9 * RF_CAP / (nrows * fmax(occ_c, 1e-9))) - 2 * fineWX;
             if (R > r_tile) R = r_tile;

@@ -73,26 +73,34 @@ struct FineConst {
     uint32_t hb, stride, wgt;        // RED address = hb + stride * bits(um + magic)
 };
 
-// Four candidates of one query: distance, bin coordinate, histogram update.  Returns the AND of
-// the four sign words (negative iff every pair is safely inside a bin); a[] = the RED addresses.
-template <bool HOME, int CAP>
-__device__ __forceinline__ int fine_quad(uint32_t ptr, const float2 &nqx2, const float2 &nqy2, const float2 &nqz2,
-                                         int ahead, const FineConst &kc, uint32_t (&a)[4], float2 (&sg)[2])
+struct FineQuad { float4 cx, cy, cz; };                           // four staged candidates: x, y, z planes
+
+template <int CAP>
+__device__ __forceinline__ FineQuad fine_load(uint32_t ptr)
 {
     constexpr uint32_t PL = CAP * 4;              // bytes between the planes
+    FineQuad c;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.cx.x), "=f"(c.cx.y), "=f"(c.cx.z), "=f"(c.cx.w) : "r"(ptr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.cy.x), "=f"(c.cy.y), "=f"(c.cy.z), "=f"(c.cy.w) : "r"(ptr + PL));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.cz.x), "=f"(c.cz.y), "=f"(c.cz.z), "=f"(c.cz.w) : "r"(ptr + 2u * PL));
+    return c;
+}
+
+// Four candidates of one query: distance, bin coordinate, histogram update.  Returns the AND of
+// the four sign words (negative iff every pair is safely inside a bin); a[] = the RED addresses.
+template <bool HOME>
+__device__ __forceinline__ int fine_quad(const FineQuad &c, const float2 &nqx2, const float2 &nqy2, const float2 &nqz2,
+                                         int ahead, const FineConst &kc, uint32_t (&a)[4], float2 (&sg)[2])
+{
     const float2 inv2 = make_float2(kc.inv_dr, kc.inv_dr), c02 = make_float2(kc.c0, kc.c0);
     const float2 magic2 = make_float2(12582912.0f, 12582912.0f), nmagic2 = make_float2(-12582912.0f, -12582912.0f);
     const float2 neg1 = make_float2(-1.0f, -1.0f), nbl2 = make_float2(kc.nbl2, kc.nbl2);
-    float4 cx, cy, cz;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cx.x), "=f"(cx.y), "=f"(cx.z), "=f"(cx.w) : "r"(ptr));
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cy.x), "=f"(cy.y), "=f"(cy.z), "=f"(cy.w) : "r"(ptr + PL));
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cz.x), "=f"(cz.y), "=f"(cz.z), "=f"(cz.w) : "r"(ptr + 2u * PL));
     float2 tt[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const float2 x2 = h ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y);
-        const float2 y2 = h ? make_float2(cy.z, cy.w) : make_float2(cy.x, cy.y);
-        const float2 z2 = h ? make_float2(cz.z, cz.w) : make_float2(cz.x, cz.y);
+        const float2 x2 = h ? make_float2(c.cx.z, c.cx.w) : make_float2(c.cx.x, c.cx.y);
+        const float2 y2 = h ? make_float2(c.cy.z, c.cy.w) : make_float2(c.cy.x, c.cy.y);
+        const float2 z2 = h ? make_float2(c.cz.z, c.cz.w) : make_float2(c.cz.x, c.cz.y);
         const float2 dx = __fadd2_rn(x2, nqx2), dy = __fadd2_rn(y2, nqy2), dz = __fadd2_rn(z2, nqz2);
         const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
         float2 d;
@@ -122,46 +130,65 @@ __device__ __forceinline__ int fine_quad(uint32_t ptr, const float2 &nqx2, const
     return __float_as_int(sg[0].x) & __float_as_int(sg[0].y) & __float_as_int(sg[1].x) & __float_as_int(sg[1].y);
 }
 
-// Walks quads [qa, qe) of the tile for one query (nq = minus the query, translated).
-// HOME: only candidates whose position is behind the query's own (`ahead` = own position -
-// position of quad qa).  A pair inside a decision band is handed to slow_fn(quad, k, addr).
-// The plain walk takes two quads per trip: the chain LDS -> FADD2 -> FFMA2 x 3 -> MUFU -> FFMA2 ->
-// FMNMX -> FADD2 x 2 -> FFMA2 x 2 -> RED is ~110 cycles long, a warp on its own issued once in six
-// cycles with one quad per trip (21 resident warps per SM: issue slots 47 % busy).
+// Walks quads [qa, qe) of the tile for TWO queries that share the window (nqa, nqb = minus the
+// queries, translated): the shared-memory data pipe was 96 % busy with one query per lane (three
+// LDS.128 of ~8 wavefronts each per four pairs -- the lanes of a warp read unrelated windows);
+// two queries get eight pairs out of the same loads.  HOME: only candidates behind each query's
+// own position (`ahead` = own position of the first query - position of quad qa; the second
+// query sits right behind the first).  A pair inside a decision band is handed to
+// slow_fn(which query, quad, k, addr).
 template <bool HOME, int CAP, class SlowFn>
-__device__ __forceinline__ void fine_walk(uint32_t planes, uint32_t qa, uint32_t qe,
-                                          float nqx, float nqy, float nqz, int ahead,
-                                          const FineConst &kc, SlowFn slow_fn)
+__device__ __forceinline__ void fine_walk2(uint32_t planes, uint32_t qa, uint32_t qe,
+                                           float3 nqa, float3 nqb, int ahead, const FineConst &kc, SlowFn slow_fn)
 {
-    const float2 nqx2 = make_float2(nqx, nqx), nqy2 = make_float2(nqy, nqy), nqz2 = make_float2(nqz, nqz);
+    const float2 ax = make_float2(nqa.x, nqa.x), ay = make_float2(nqa.y, nqa.y), az = make_float2(nqa.z, nqa.z);
+    const float2 bx = make_float2(nqb.x, nqb.x), by = make_float2(nqb.y, nqb.y), bz = make_float2(nqb.z, nqb.z);
     const uint32_t end = planes + 16u * qe;
-    uint32_t ptr = planes + 16u * qa;
     // (the divergent region stays INSIDE the loop: a lane that left the loop for its band pair
-    // would walk the rest of its window on its own -- measured 15 of 32 lanes active)
-    auto slow4 = [&](uint32_t at, const uint32_t (&a)[4], const float2 (&sg)[2]) {
+    // would walk the rest of its window on its own)
+    auto slow4 = [&](int which, uint32_t at, const uint32_t (&a)[4], const float2 (&sg)[2]) {
         const uint32_t quad = (at - planes) >> 4;
-        if (__float_as_int(sg[0].x) >= 0) slow_fn(quad, 0, a[0]);
-        if (__float_as_int(sg[0].y) >= 0) slow_fn(quad, 1, a[1]);
-        if (__float_as_int(sg[1].x) >= 0) slow_fn(quad, 2, a[2]);
-        if (__float_as_int(sg[1].y) >= 0) slow_fn(quad, 3, a[3]);
+        if (__float_as_int(sg[0].x) >= 0) slow_fn(which, quad, 0, a[0]);
+        if (__float_as_int(sg[0].y) >= 0) slow_fn(which, quad, 1, a[1]);
+        if (__float_as_int(sg[1].x) >= 0) slow_fn(which, quad, 2, a[2]);
+        if (__float_as_int(sg[1].y) >= 0) slow_fn(which, quad, 3, a[3]);
     };
-    if (!HOME) {
-        for (; ptr + 32u <= end; ptr += 32u) {
+    if (HOME) {
+        for (uint32_t ptr = planes + 16u * qa; ptr < end; ptr += 16u, ahead -= 4) {
+            const FineQuad c = fine_load<CAP>(ptr);
             uint32_t a[4], b[4];
             float2 sa[2], sb[2];
-            const int na = fine_quad<false, CAP>(ptr, nqx2, nqy2, nqz2, 0, kc, a, sa);
-            const int nb = fine_quad<false, CAP>(ptr + 16u, nqx2, nqy2, nqz2, 0, kc, b, sb);
+            const int na = fine_quad<true>(c, ax, ay, az, ahead, kc, a, sa);
+            const int nb = fine_quad<true>(c, bx, by, bz, ahead + 1, kc, b, sb);
             if ((na & nb) >= 0) {
-                if (na >= 0) slow4(ptr, a, sa);
-                if (nb >= 0) slow4(ptr + 16u, b, sb);
+                if (na >= 0) slow4(0, ptr, a, sa);
+                if (nb >= 0) slow4(1, ptr, b, sb);
             }
         }
-    }
-    for (; ptr < end; ptr += 16u, ahead -= 4) {
-        uint32_t a[4];
-        float2 sa[2];
-        const int na = fine_quad<HOME, CAP>(ptr, nqx2, nqy2, nqz2, ahead, kc, a, sa);
-        if (na >= 0) slow4(ptr, a, sa);
+    } else {
+        // The windows of a warp's lanes lie anywhere in the tile: eight lanes of a quarter warp hit
+        // the eight 16-byte bank groups at random (measured: 9 wavefronts per LDS.128, the data pipe
+        // 88 % busy).  The order within a window is free, so lane l starts at the first quad of its
+        // window that lies in bank group l mod 8 and wraps around at the end: lanes that advance
+        // together stay in different groups (until they wrap, windows of a warp being equally long).
+        const uint32_t first = planes + 16u * qa;
+        const uint32_t n = qe - qa;
+        uint32_t rot = ((threadIdx.x & 7u) - (first >> 4)) & 7u;
+        if (rot >= n) rot = 0u;
+        uint32_t ptr = first + 16u * rot;
+        for (uint32_t left = n; left; --left) {
+            const FineQuad c = fine_load<CAP>(ptr);
+            uint32_t a[4], b[4];
+            float2 sa[2], sb[2];
+            const int na = fine_quad<false>(c, ax, ay, az, 0, kc, a, sa);
+            const int nb = fine_quad<false>(c, bx, by, bz, 0, kc, b, sb);
+            if ((na & nb) >= 0) {
+                if (na >= 0) slow4(0, ptr, a, sa);
+                if (nb >= 0) slow4(1, ptr, b, sb);
+            }
+            ptr += 16u;
+            if (ptr == end) ptr = first;
+        }
     }
 }
 
@@ -186,9 +213,9 @@ template <int NR> struct FineUnit {
 constexpr unsigned FINE_OVER_TILE = 2u, FINE_OVER_LIST = 4u, FINE_OVER_QUERIES = 8u;
 
 // Planner: everything the walk needs to know, computed with nothing but bookkeeping resident
-// (no tile: nine CTAs per SM hide the chains of dependent loads that cost the fused kernel
-// 73 000 cycles per CTA): row descriptors, and the (query, row) windows as records
-//   quads | first quad << 7 | query << 17 | row << 25
+// (no tile: six CTAs per SM hide the chains of dependent loads that cost the fused kernel
+// 73 000 cycles per CTA): row descriptors, and the (pair of queries, row) windows as records
+//   quads | first quad << 7 | pair << 17 | row << 25
 // counting-sorted by length, longest first, home-row records behind the others.
 template <bool SELF, int T>
 __global__ void __launch_bounds__(T, 6)
@@ -274,8 +301,15 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
         if (tid == 0) unit.h.nq = 0u;
         return;
     }
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((uint32_t)tid < nq_all) q = q_atoms[qs0 + tid];
+    // A thread plans for a PAIR of neighbouring queries (2 * pair, 2 * pair + 1: the walker evaluates
+    // both against the same candidates) and for one half of the stencil rows.
+    constexpr int HALF = T / 2, NRH = (NR + 1) / 2;
+    const uint32_t pair = (uint32_t)(tid % HALF), npairs = (nq_all + 1u) >> 1;
+    const int rlo = (tid / HALF) * NRH;
+    const bool has_a = pair < npairs && tid < 2 * HALF, has_b = has_a && 2u * pair + 1u < nq_all;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), qb = q;
+    if (has_a) q = q_atoms[qs0 + 2u * pair];
+    if (has_b) qb = q_atoms[qs0 + 2u * pair + 1u];
     // ---- step 2: row descriptors; extended position of every staged fine cell ----
     auto row_lens = [&](int r, uint32_t &nL, uint32_t &nM, uint32_t &nR) {
         const bool home = SELF && r == 0;
@@ -342,41 +376,56 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
     unsigned over = 0u;
     if (fill > (uint32_t)cap) over |= FINE_OVER_TILE;
     if (nq_all > (uint32_t)T) over |= FINE_OVER_QUERIES;
-    // ---- this thread's windows: first quad | quads << 10, one word per row ----
-    uint32_t win[NR];
+    // ---- this thread's windows (the union of the two queries' windows): first quad | quads << 10 ----
+    uint32_t win[NRH];
     {
-        const uint32_t pos = (uint32_t)tid;
-        int e0 = 0, e1 = nh;                                       // home fine cell: s_qraw[e0] <= qs0 + pos < s_qraw[e1]
-        while (e1 - e0 > 1) {
-            const int mid = (e0 + e1) >> 1;
-            if (s_qraw[mid] <= qs0 + pos) e0 = mid; else e1 = mid;
-        }
-        const int ce = e0 + WX;                                    // its index among the staged cells
+        const uint32_t pos = 2u * pair;
+        auto home_cell = [&](uint32_t at) {                        // fine cell of the query at position `at`
+            int e0 = 0, e1 = nh;                                   // s_qraw[e0] <= qs0 + at < s_qraw[e1]
+            while (e1 - e0 > 1) {
+                const int mid = (e0 + e1) >> 1;
+                if (s_qraw[mid] <= qs0 + at) e0 = mid; else e1 = mid;
+            }
+            return e0;
+        };
+        const int ea = home_cell(pos), eb = has_b ? home_cell(pos + 1u) : ea;
         const float reach2 = fp.reach * fp.reach;
+        auto window = [&](const float4 &qq, int e0, const uint32_t *eo, const float4 &g, uint32_t &lo, uint32_t &hi) {
+            const float gy = fmaf(g.x, qq.y, g.y), gz = fmaf(g.z, qq.z, g.w);
+            const float h2 = fmaf(-gy, gy, fmaf(-gz, gz, reach2));
+            float h;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(fmaxf(h2, 0.0f)));
+            int k = (int)(h * inv_wx) + 1;
+            k = k > WX ? WX : k;
+            lo = eo[e0 + WX - k];
+            hi = h2 > 0.0f ? eo[e0 + WX + k + 1] : lo;
+        };
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            win[r] = 0u;
-            if ((uint32_t)tid < nq_all && !over) {
+        for (int i = 0; i < NRH; ++i) {
+            const int r = rlo + i;
+            win[i] = 0u;
+            if (r < NR && has_a && !over) {
                 const bool home = SELF && r == 0;
                 const uint32_t *eo = eoff + r * ne1;
                 const float4 g = s_gap[r];
                 uint32_t lo, hi;
                 if (home) {
-                    lo = eo[e0];
-                    hi = eo[WX] + pos;                             // the query's own extended position
+                    lo = eo[ea];
+                    hi = eo[WX] + pos + (has_b ? 1u : 0u);         // the own extended position of the pair's last query
                 } else {
-                    const float gy = fmaf(g.x, q.y, g.y), gz = fmaf(g.z, q.z, g.w);
-                    const float h2 = fmaf(-gy, gy, fmaf(-gz, gz, reach2));
-                    float h;
-                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(fmaxf(h2, 0.0f)));
-                    int k = (int)(h * inv_wx) + 1;
-                    k = k > WX ? WX : k;
-                    lo = eo[ce - k];
-                    hi = h2 > 0.0f ? eo[ce + k + 1] : lo;
+                    window(q, ea, eo, g, lo, hi);
+                    if (has_b) {
+                        uint32_t lo2, hi2;
+                        window(qb, eb, eo, g, lo2, hi2);
+                        if (lo2 < hi2) {
+                            if (lo < hi) { lo = min(lo, lo2); hi = max(hi, hi2); }
+                            else { lo = lo2; hi = hi2; }
+                        }
+                    }
                 }
                 if (lo < hi) {
                     const uint32_t qa = (s_base[r] >> 2) + (lo >> 2), qe = (s_base[r] >> 2) + ((hi + 3u) >> 2);
-                    win[r] = qa | ((qe - qa) << 10);
+                    win[i] = qa | ((qe - qa) << 10);
                 }
             }
         }
@@ -384,18 +433,22 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
     // records of this thread: emit(bucket, record); windows longer than RF_WMAX quads are split
     auto records = [&](auto emit) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            if (!win[r]) continue;
+        for (int i = 0; i < NRH; ++i) {
+            if (!win[i]) continue;
+            const int r = rlo + i;
             const bool home = SELF && r == 0;
-            const uint32_t qa = win[r] & 1023u, qe = qa + (win[r] >> 10);
+            const uint32_t qa = win[i] & 1023u, qe = qa + (win[i] >> 10);
             for (uint32_t j = qa; j < qe; j += RF_WMAX) {
                 const uint32_t len = min((uint32_t)RF_WMAX, qe - j);
                 emit((home ? (uint32_t)RF_WMAX : 0u) + (uint32_t)RF_WMAX - len,
-                     len | (j << 7) | ((uint32_t)tid << 17) | ((uint32_t)r << 25));
+                     len | (j << 7) | (pair << 17) | ((uint32_t)r << 25));
             }
         }
     };
-    // ---- counting sort by length (per warp counters: the lanes of a warp only contend with each other) ----
+    // ---- counting sort by length, longest first (per warp counters: the lanes of a warp only
+    // contend with each other).  (Tried: eight streams by first quad mod 8, interleaved, so that a
+    // quarter warp reads eight different bank groups -- conflicts gone, but the lengths within a warp
+    // matched less well: 24.7 instead of 30.6 active lanes.  The walker rotates its windows instead.) ----
     records([&](uint32_t b, uint32_t) { atomicAdd(&s_cnt[warp][b], 1u); });
     __syncthreads();
     if (warp == 0) {
@@ -429,9 +482,7 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
     const uint32_t hstart = s_tot[0], nrec = s_tot[1];
     if (nrec > (uint32_t)list_cap) over |= FINE_OVER_LIST;
     uint32_t *list = lists + ((uint64_t)f * gridDim.x + blockIdx.x) * (uint64_t)list_cap;
-    if (!over) {
-        records([&](uint32_t b, uint32_t rec) { list[atomicAdd(&s_cnt[warp][b], 1u)] = rec; });
-    }
+    if (!over) records([&](uint32_t b, uint32_t rec) { list[atomicAdd(&s_cnt[warp][b], 1u)] = rec; });
     __syncthreads();
     if (!over) {
         // (cursors have advanced to the ends of their runs: the last plain cursor is the plain total)
@@ -563,23 +614,28 @@ fine_walk_kernel(const float4 *__restrict__ q_atoms, const float4 *__restrict__ 
         nxt = __shfl_sync(0xffffffffu, nxt, 0);
         const uint32_t rec_next = 32u * nxt + lane < nrec ? list[32u * nxt + lane] : 0u;
         const bool home = SELF && 32u * (uint32_t)item >= hstart;  // uniform
-        const uint32_t len = rec & 127u, qa = (rec >> 7) & 1023u, qi = (rec >> 17) & 255u;
+        const uint32_t len = rec & 127u, qa = (rec >> 7) & 1023u, pair = (rec >> 17) & 255u;
         const int r = (int)(rec >> 25);
         const FineRowC fc = s_u.c[r];
-        float qx, qy, qz;
+        const uint32_t qi = 2u * pair;
+        const bool has_b = qi + 1u < nq;
+        float3 qa3, qb3;
         if (SELF) {
             const uint32_t at = tile0 + 4u * (own0 + qi);
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qx) : "r"(at));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qy) : "r"(at + CAP * 4u));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qz) : "r"(at + 2u * CAP * 4u));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qa3.x) : "r"(at));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qa3.y) : "r"(at + CAP * 4u));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qa3.z) : "r"(at + 2u * CAP * 4u));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qb3.x) : "r"(at + 4u));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qb3.y) : "r"(at + CAP * 4u + 4u));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qb3.z) : "r"(at + 2u * CAP * 4u + 4u));
         } else {
-            const float4 qq = s_q[SELF ? 0 : qi];
-            qx = qq.x; qy = qq.y; qz = qq.z;
+            const float4 q0 = s_q[SELF ? 0 : qi], q1 = s_q[SELF ? 0 : min(qi + 1u, nq - 1u)];
+            qa3 = make_float3(q0.x, q0.y, q0.z);
+            qb3 = make_float3(q1.x, q1.y, q1.z);
         }
-        qy -= fc.sy;
-        qz -= fc.sz;
+        if (!has_b) qb3 = make_float3(-QUAD_FAR, -QUAD_FAR, -QUAD_FAR);      // nobody there: every candidate misses
         const uint32_t qslot = qs0 + qi;
-        auto slow_fn = [&](uint32_t quad, int k, uint32_t addr) {
+        auto slow_fn = [&](int which, uint32_t quad, int k, uint32_t addr) {
             // out of the bin the FP32 path chose; float64 decides (a sentinel is never inside a band)
             asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(0u - kc.wgt) : "memory");
             const FineRowA fa = s_u.a[r];
@@ -587,13 +643,15 @@ fine_walk_kernel(const float4 *__restrict__ q_atoms, const float4 *__restrict__ 
             const uint32_t p = 4u * quad + (uint32_t)k - fa.base;
             const uint32_t cslot = p < fb.end0 ? fa.g0 + p : (p < fb.end1 ? fa.g1 + (p - fb.end0) : fa.g2 + (p - fb.end1));
             const uint32_t at = atomicAdd(nslow, 1u);
-            if (at < (uint32_t)RF_SLOW) slowq[at] = make_uint2(qslot, cslot);
-            else quad_exact<SELF, Sink>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, qslot, cslot, f);
+            if (at < (uint32_t)RF_SLOW) slowq[at] = make_uint2(qslot + (uint32_t)which, cslot);
+            else quad_exact<SELF, Sink>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, qslot + (uint32_t)which, cslot, f);
         };
-        if (home)                                                  // candidates behind the query's own position only
-            fine_walk<true, CAP>(tile0, qa, qa + len, -qx, -qy, -qz, (int)(own0 + qi) - (int)(4u * qa), kc, slow_fn);
+        const float3 na3 = make_float3(-qa3.x, -(qa3.y - fc.sy), -(qa3.z - fc.sz));
+        const float3 nb3 = make_float3(-qb3.x, -(qb3.y - fc.sy), -(qb3.z - fc.sz));
+        if (home)                                                  // candidates behind each query's own position only
+            fine_walk2<true, CAP>(tile0, qa, qa + len, na3, nb3, (int)(own0 + qi) - (int)(4u * qa), kc, slow_fn);
         else
-            fine_walk<false, CAP>(tile0, qa, qa + len, -qx, -qy, -qz, 0, kc, slow_fn);
+            fine_walk2<false, CAP>(tile0, qa, qa + len, na3, nb3, 0, kc, slow_fn);
         __syncwarp();
         if (*nslow >= (uint32_t)(RF_SLOW - 8)) drain();            // (32 at a time: an evaluation by two lanes costs as much)
         item = (int)nxt;
