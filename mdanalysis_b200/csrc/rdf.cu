@@ -744,11 +744,13 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             if (!same) MDA_CUDA(cudaMemcpyAsync(&bad[1], ql.inconsistent(), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             MDA_CUDA(cudaStreamSynchronize(st));
             if (bad[0] | bad[1]) {
+                if (getenv("MDAGPU_DEBUG")) fprintf(stderr, "mdagpu: rdf cell list has folded atoms, piece of %llu frames\n", (unsigned long long)fc);
                 if (mic == MIC_TRICLINIC) tv.row = 0;
                 else {
                     rc = rdf_accumulate_impl(a_dev, na, same ? nullptr : b_dev, nb, fc, boxes_per_frame ? box6 + 6 * f0 : box6,
                                              boxes_per_frame ? h9 + 9 * f0 : h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
-                                             use_grid, thresholds, nbins, r_lo, r_hi, excl_a, excl_b, ids_a_host, ids_b_host,
+                                             use_grid, thresholds, nbins, r_lo, r_hi, (same && !report_self) ? 1 : excl_a,
+                                         (same && !report_self) ? 1 : excl_b, ids_a_host, ids_b_host,
                                              cnt.as<unsigned long long>(), per_site, MDAGPU_DEVICE, stream, 1);
                     if (rc) return rc;
                     if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
@@ -810,9 +812,11 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             MDA_CUDA(cudaMemcpyAsync(&over, oflag.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             MDA_CUDA(cudaStreamSynchronize(st));
             if (over) {
+                if (getenv("MDAGPU_DEBUG")) fprintf(stderr, "mdagpu: rdf planner declined (flags %u), piece of %llu frames\n", over, (unsigned long long)fc);
                 rc = rdf_accumulate_impl(a_dev, na, same ? nullptr : b_dev, nb, fc, boxes_per_frame ? box6 + 6 * f0 : box6,
                                          boxes_per_frame ? h9 + 9 * f0 : h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
-                                         use_grid, thresholds, nbins, r_lo, r_hi, excl_a, excl_b, ids_a_host, ids_b_host,
+                                         use_grid, thresholds, nbins, r_lo, r_hi, (same && !report_self) ? 1 : excl_a,
+                                         (same && !report_self) ? 1 : excl_b, ids_a_host, ids_b_host,
                                          cnt.as<unsigned long long>(), per_site, MDAGPU_DEVICE, stream, 2);
                 if (rc) return rc;
                 if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
