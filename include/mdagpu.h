@@ -280,6 +280,25 @@ MDAGPU_API int mdagpu_contacts_self(const float *xyz, uint64_t n, uint64_t nfram
                          unsigned long long *counts, int32_t *degree, int space,
                          mdagpu_stream_t stream);
 
+/* ---- trajectory ingest: the step in front of the path ---- */
+
+/* Bulk DCD reader: coordinates/DCD.py:279-344 (DCDReader.timeseries) ->
+ * lib/formats/libdcd.pyx:583-700 (DCDFile.readframes), C side lib/formats/include/readdcd.h.
+ * Host code; CHARMM and X-PLOR flavours, either endianness, 4-byte record markers,
+ * no fixed atoms. */
+typedef struct mdagpu_dcd mdagpu_dcd;
+MDAGPU_API int mdagpu_dcd_open(const char *path, mdagpu_dcd **out);
+MDAGPU_API void mdagpu_dcd_close(mdagpu_dcd *d);
+/* header fields (libdcd.pyx:279-330 `header`): natoms, number of frames (from the file
+ * size, as the reference), unit cell records present, ISTART, NSAVC, DELTA, CHARMM version */
+MDAGPU_API int mdagpu_dcd_header(const mdagpu_dcd *d, int64_t *natoms, int64_t *nframes, int *has_cell,
+                      int32_t *istart, int32_t *nsavc, double *delta, int *charmm);
+/* frames range(start, stop, step) of atoms `indices` (NULL: all) into
+ *   xyz       float32 [n, nsel, 3] ('fac' order; pinned memory recommended)
+ *   unitcell  float64 [n, 6] in the FILE's order [A, gamma, B, beta, alpha, C], or NULL */
+MDAGPU_API int mdagpu_dcd_readframes(mdagpu_dcd *d, int64_t start, int64_t stop, int64_t step,
+                          const int64_t *indices, int64_t nsel, float *xyz, double *unitcell);
+
 #ifdef __cplusplus
 }
 #endif

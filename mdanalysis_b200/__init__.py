@@ -16,10 +16,10 @@ There is no CPU fallback: every numerical result comes from libmdagpu.so.
 from . import _cabi
 from .frames import FrameBlock
 from . import lib, analysis, parallel, register  # noqa: F401
-from .adapters import run_on_gpu
+from .adapters import cuda_backend, gpu_enabled, run_on_gpu
 
 __version__ = "0.1.0"
-__all__ = ["FrameBlock", "lib", "analysis", "parallel", "register", "library_path", "run_on_gpu"]
+__all__ = ["FrameBlock", "lib", "analysis", "parallel", "register", "library_path", "run_on_gpu", "cuda_backend", "gpu_enabled"]
 
 
 def library_path():

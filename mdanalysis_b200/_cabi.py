@@ -61,6 +61,11 @@ SIGNATURES = {
     "mdagpu_rdf_sites_accumulate": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,
                                          _d, _d, _vp, _i, _vp]),
     "mdagpu_contacts_self": (_i, [_vp, _u64, _u64, _i, _vp, _d, _d, _vp, _vp, _i, _vp]),
+    "mdagpu_dcd_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "mdagpu_dcd_close": (None, [_vp]),
+    "mdagpu_dcd_header": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(_i), C.POINTER(C.c_int32),
+                               C.POINTER(C.c_int32), C.POINTER(_d), C.POINTER(_i)]),
+    "mdagpu_dcd_readframes": (_i, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, _vp]),
 }
 
 _lib = None

@@ -37,10 +37,21 @@ def _frames_of(analysis, start, stop, step, frames):
 
 
 def _block(atomgroup, idx):
-    blk = FrameBlock.from_atomgroup(atomgroup)
-    if len(idx) != blk.n_frames or not np.array_equal(idx, np.arange(blk.n_frames)):
-        blk = blk.slice_frames(idx)
-    return blk
+    """The atoms of ``atomgroup`` for the frames ``idx`` only: the frame range (and the atom
+    selection) are pushed down to the reader, nothing else is read."""
+    idx = np.asarray(idx, dtype=np.int64)
+    if len(idx) > 1 and np.all(np.diff(idx) == idx[1] - idx[0]) and idx[1] > idx[0]:
+        st = int(idx[1] - idx[0])
+        return FrameBlock.from_atomgroup(atomgroup, start=int(idx[0]), stop=int(idx[-1]) + 1, step=st)
+    if len(idx) == 1:
+        return FrameBlock.from_atomgroup(atomgroup, start=int(idx[0]), stop=int(idx[0]) + 1, step=1)
+    return FrameBlock.from_atomgroup(atomgroup, frames=idx)
+
+
+def _compact(universe, index_lists):
+    """AtomGroup of the union of ``index_lists`` and the lists re-expressed in its numbering."""
+    used = np.unique(np.concatenate([np.asarray(ix, dtype=np.int64) for ix in index_lists]))
+    return universe.atoms[used], [np.searchsorted(used, np.asarray(ix, dtype=np.int64)) for ix in index_lists]
 
 
 def _finish(analysis, gpu):
@@ -86,20 +97,25 @@ def _run_interrdf_s(an, idx, device):
 def _run_rmsd(an, idx, device):
     from .analysis.rms import RMSD
     mob_u, ref_u = an.atomgroup.universe, an.reference.universe
-    blk = _block(mob_u.atoms, idx)
-    blk.masses = np.asarray(mob_u.atoms.masses, dtype=np.float64) if hasattr(mob_u.atoms, "masses") else None
+    # the reference structure is a snapshot of frame ref_frame, taken before anything else moves a reader
     cur = ref_u.trajectory.ts.frame
     try:
         ref_u.trajectory[an.ref_frame]
-        refblk = FrameBlock(ref_u.atoms.positions.copy()[None],
-                            masses=np.asarray(ref_u.atoms.masses, dtype=np.float64) if hasattr(ref_u.atoms, "masses") else None)
+        ref_pos = ref_u.atoms.positions.copy()
     finally:
         ref_u.trajectory[cur]
+    gsel = getattr(an, "_groupselections_atoms", [])
+    # only the atoms that take part are read: the fitted selection and the group selections
+    mob_ag, mob_lists = _compact(mob_u, [an.mobile_atoms.indices] + [g["mobile"].indices for g in gsel])
+    ref_used, ref_lists = _compact(ref_u, [an.ref_atoms.indices] + [g["reference"].indices for g in gsel])
+    blk = _block(mob_ag, idx)
+    blk.masses = np.asarray(mob_ag.masses, dtype=np.float64) if hasattr(mob_u.atoms, "masses") else None
+    refblk = FrameBlock(ref_pos[ref_used.indices][None],
+                        masses=np.asarray(ref_used.masses, dtype=np.float64) if hasattr(ref_u.atoms, "masses") else None)
     if device:
         blk = blk.to_device()
-    groups = [{"mobile": g["mobile"].indices, "reference": g["reference"].indices}
-              for g in getattr(an, "_groupselections_atoms", [])]
-    gpu = RMSD(blk, refblk, select={"mobile": an.mobile_atoms.indices, "reference": an.ref_atoms.indices},
+    groups = [{"mobile": m, "reference": r} for m, r in zip(mob_lists[1:], ref_lists[1:])]
+    gpu = RMSD(blk, refblk, select={"mobile": mob_lists[0], "reference": ref_lists[0]},
                groupselections=groups or None, weights=an.weights,
                weights_groupselections=an.weights_groupselections, tol_mass=an.tol_mass, ref_frame=0).run()
     an.results.rmsd = gpu.results.rmsd
@@ -111,11 +127,13 @@ def _run_aligntraj(an, idx, device):
     if an.filename is not None:
         raise NotImplementedError("AlignTraj on the GPU path rewrites an in-memory trajectory (in_memory=True)")
     mob_u, ref_u = an.mobile.universe, an.ref_atoms.universe
+    # AlignTraj._prepare fits to the reference atoms as they are when run() is called
+    # (analysis/align.py:836-845): snapshot them before the bulk read touches a reader
+    refblk = FrameBlock(ref_u.atoms.positions.copy()[None])
     traj = mob_u.trajectory
     arr = traj.get_array()                                   # MemoryReader: the coordinates themselves
     order = traj.stored_order
     blk = _block(mob_u.atoms, idx)
-    refblk = FrameBlock(ref_u.atoms.positions.copy()[None])
     if device:
         blk = blk.to_device()
     w = an._weights
@@ -212,33 +230,132 @@ def run_on_gpu(analysis, start=None, stop=None, step=None, frames=None, device=T
     return runner(analysis, idx, device)
 
 
+def _aggregators():
+    """How the per-part results of each supported class merge (``ResultsGroup.merge``,
+    ``analysis/results.py:185-226``): histograms add up, per-frame series stack."""
+    from MDAnalysis.analysis.results import ResultsGroup as RG
+
+    def same(arrs):                      # identical in every part (bin edges and centres)
+        return arrs[0]
+
+    def sum_lists(parts):                # InterRDF_s: a list of [n_i, n_j, nbins] arrays per part
+        return [np.sum(np.array(x), axis=0) for x in zip(*parts)]
+
+    def first_list(parts):
+        return parts[0]
+
+    return {
+        "RMSD": {"rmsd": RG.ndarray_vstack},
+        "InterRDF": {"count": RG.ndarray_sum, "volume_cum": RG.ndarray_sum, "edges": same, "bins": same},
+        "InterRDF_s": {"count": sum_lists, "volume_cum": RG.ndarray_sum, "edges": same, "bins": same,
+                       "indices": first_list},
+        "Contacts": {"timeseries": RG.ndarray_vstack},
+        "AlignTraj": {"rmsd": RG.ndarray_hstack},
+    }
+
+
+def gpu_enabled(analysis):
+    """Make a constructed reference analysis acceptable to ``AnalysisBase.run(backend=...)``.
+
+    ``InterRDF``, ``InterRDF_s``, ``AlignTraj`` and ``Contacts`` declare
+    ``_analysis_algorithm_is_parallelizable = False`` and ``_configure_backend`` turns every
+    non-serial executor away (``analysis/base.py:590-654``).  This is the plug point of SURVEY.md
+    section 8(b)4: the object is re-classed to a subclass that sets the flag, names the built-in
+    backends as supported (so a custom executor needs ``unsupported_backend=True``, as for ``RMSD``),
+    supplies ``_get_aggregator`` (``ndarray_sum`` for counts, ``ndarray_vstack`` / ``hstack`` for
+    series) and a ``_conclude`` that works on the merged results.  Usage::
+
+        rdf = gpu_enabled(InterRDF(ow, ow, nbins=150, range=(0, 15)))
+        rdf.run(backend=cuda_backend(8), unsupported_backend=True)
+    """
+    from MDAnalysis.analysis.results import ResultsGroup
+
+    cls = type(analysis)
+    name = cls.__name__
+    lookup = _aggregators().get(name)
+    if lookup is None:
+        raise TypeError(f"gpu_enabled(): {cls.__module__}.{name} has no frame-parallel GPU path; "
+                        f"supported: {sorted(_aggregators())}")
+    if getattr(cls, "_mdagpu_enabled", False):
+        return analysis
+
+    def get_supported_backends(klass):
+        return ("serial", "multiprocessing", "dask")
+
+    def _get_aggregator(self):
+        return ResultsGroup(lookup=dict(lookup))
+
+    def _conclude(self):
+        if name in ("InterRDF", "InterRDF_s"):
+            self.volume_cum = float(np.sum(self.results.pop("volume_cum")))
+            return cls._conclude(self)
+        if name == "AlignTraj":
+            self._writer.close()
+            return None
+        if name == "Contacts":
+            self.results.timeseries = np.asarray(self.results.timeseries, dtype=float)
+            return None
+        return cls._conclude(self)
+
+    sub = type(name, (cls,), {"_analysis_algorithm_is_parallelizable": True, "_mdagpu_enabled": True,
+                              "get_supported_backends": classmethod(get_supported_backends),
+                              "_get_aggregator": _get_aggregator, "_conclude": _conclude,
+                              "__module__": cls.__module__})
+    analysis.__class__ = sub
+    return analysis
+
+
 def cuda_backend(n_workers: int = 1):
     """A ``BackendBase`` executor for ``AnalysisBase.run(backend=..., unsupported_backend=True)``
     (``analysis/backends.py:43-157``, ``analysis/base.py:590-695``).
 
     ``apply(func, computations)`` receives ``func = partial(analysis._compute, ...)`` and one
-    ``[(result index, frame number), ...]`` array per part; each part is computed by
-    ``run_on_gpu`` on a shallow copy of the analysis object, which then carries ``frames``,
-    ``times`` and ``results`` for the reference's own aggregation (``_get_aggregator``,
-    ``ResultsGroup.merge``).  Only classes that declare themselves parallelizable get this far
-    in the reference (``RMSD`` on this path); for the others use ``run_on_gpu`` directly.
+    ``[(result index, frame number), ...]`` array per part (``np.array_split`` of the frames,
+    ``base.py:579-588``); each part is computed by ``run_on_gpu`` on a shallow copy of the analysis
+    object, which then carries ``frames``, ``times`` and ``results`` for the reference's own
+    aggregation (``_get_aggregator``, ``ResultsGroup.merge``).  ``n_workers`` parts run at the same
+    time, worker ``k`` on CUDA device ``k mod device_count`` (one host thread per worker: the CUDA
+    runtime's current device is per thread, the C ABI releases the GIL, and no process is forked --
+    a CUDA context does not survive ``fork``, which is why the reference's ``multiprocessing``
+    backend cannot drive this library).  ``RMSD`` gets here as it is; for ``InterRDF``,
+    ``InterRDF_s``, ``AlignTraj`` and ``Contacts`` wrap the object with ``gpu_enabled`` first.
     """
     import copy
+    from concurrent.futures import ThreadPoolExecutor
 
     from MDAnalysis.analysis.backends import BackendBase
     from MDAnalysis.analysis.results import Results
 
     class CudaBackend(BackendBase):
         def apply(self, func, computations):
+            import torch
             analysis = getattr(getattr(func, "func", func), "__self__", None)
             if analysis is None:
                 raise ValueError("CudaBackend.apply: expected a bound AnalysisBase._compute")
-            out = []
-            for indexed_frames in computations:
+            ndev = max(1, torch.cuda.device_count())
+            keep = None
+            if getattr(type(analysis), "_mdagpu_enabled", False):
+                keep = set(_aggregators()[type(analysis).__name__])
+
+            def work(job):
+                k, indexed_frames = job
                 part = copy.copy(analysis)
                 part.results = Results()
                 frames = np.asarray(indexed_frames)[:, 1] if len(indexed_frames) else np.empty(0, dtype=int)
-                out.append(run_on_gpu(part, frames=frames))
-            return out
+                with torch.cuda.device(k % ndev):
+                    run_on_gpu(part, frames=frames)
+                if keep is not None:                       # raw, mergeable quantities only
+                    if "volume_cum" in keep:
+                        part.results["volume_cum"] = np.float64(part.volume_cum)
+                    for key in [key for key in part.results if key not in keep]:
+                        del part.results[key]
+                return part
+
+            jobs = list(enumerate(computations))
+            workers = max(1, min(int(self.n_workers), len(jobs)))
+            if workers == 1:
+                return [work(j) for j in jobs]
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                return list(pool.map(work, jobs))
 
     return CudaBackend(n_workers=n_workers)

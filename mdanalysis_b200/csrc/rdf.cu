@@ -829,16 +829,13 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             HistSinkFine<224> sink = { thr_in.as<double>(), cnt.as<unsigned long long>(), nbins, ls, c0, inv_dr, dv.band_lim };
             const size_t hist = ((((size_t)(nbins + 2) << ls) * sizeof(uint32_t)) + 15) & ~(size_t)15;
             const size_t total = hist + 3 * (size_t)RF_CAP * sizeof(float);
-            {
-                static bool attr_set = false;
-                if (!attr_set) {
-                    MDA_CUDA(cudaFuncSetAttribute(fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                    MDA_CUDA(cudaFuncSetAttribute(fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                    attr_set = true;
-                }
-            }
+            // (per device and cheap: set on every call, like the other kernels of this file)
+            if (same)
+                MDA_CUDA(cudaFuncSetAttribute(fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+            else
+                MDA_CUDA(cudaFuncSetAttribute(fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
             const BoxParams bx = fgs[boxes_per_frame ? f0 : 0].box;
             // (per-frame boxes: the walker only needs the box for the rare float64 evaluations; frames of
             // one call that differ in their box are binned frame by frame)

@@ -11,9 +11,15 @@ real MDAnalysis AtomGroup when MDAnalysis is importable.
 """
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 
 from ._cabi import is_tensor
+
+# a generic reader is moved frame by frame: one ingest at a time (the multi-GPU executor of
+# adapters.py reads the parts of a run from several threads)
+_READER_LOCK = threading.Lock()
 
 
 class FrameBlock:
@@ -88,22 +94,88 @@ class FrameBlock:
                           self.times, self.masses)
 
     @classmethod
-    def from_atomgroup(cls, atomgroup, start=None, stop=None, step=None):
-        """Bulk ingest from an MDAnalysis AtomGroup (needs MDAnalysis)."""
+    def from_atomgroup(cls, atomgroup, start=None, stop=None, step=None, frames=None):
+        """Bulk ingest of the atoms of ``atomgroup`` for the frames ``[start:stop:step]`` (or the
+        explicit ``frames``) of its universe's trajectory -- the GPU twin of the reference's
+        per-frame loop (``analysis/base.py:515-523``).
+
+        * ``DCDReader``: the native bulk reader (``coordinates/dcd.py`` -> ``csrc/dcd.cu``) on the
+          reader's file: only the selected atoms of the selected frames are read, straight into
+          pinned memory; unit cells and times come out of the same read (``coordinates/DCD.py:211-256``).
+        * ``MemoryReader``: the coordinate array itself (``coordinates/memory.py:480-484``), unit
+          cells from ``dimensions_array``, ``time = frame * dt`` (``memory.py:606``).
+        * any other reader (or a reader with on-the-fly transformations): ``timeseries`` with the
+          frame range pushed down, unit cells and times from one pass over those frames.
+
+        The reader is left on the frame it was on (the reference's analyses snapshot
+        ``ts`` where ``run()`` is called, e.g. ``analysis/align.py:836-845``)."""
         u = atomgroup.universe
         traj = u.trajectory
-        sl = slice(start, stop, step)
-        frames = np.arange(len(traj))[sl]
-        # one bulk read of every frame (MemoryReader.timeseries has inclusive-stop semantics and
-        # rejects stop=None, coordinates/memory.py:545-567), sliced here
-        pos = np.asarray(traj.timeseries(atomgroup, order="fac"))[sl]
-        dims, times = [], []
-        for ts in traj[sl]:
-            dims.append(None if ts.dimensions is None else np.array(ts.dimensions, dtype=np.float32))
-            times.append(ts.time)
-        dimensions = None if any(d is None for d in dims) else np.stack(dims)
+        n_all = len(traj)
+        if frames is not None:
+            fidx = np.asarray(frames, dtype=np.int64)
+            regular = None
+        else:
+            regular = slice(start, stop, step)
+            fidx = np.arange(n_all)[regular]
+        aidx = np.asarray(atomgroup.indices, dtype=np.int64)
+        whole = len(aidx) == u.atoms.n_atoms and bool(np.array_equal(aidx, np.arange(len(aidx))))
         masses = getattr(atomgroup, "masses", None)
-        return cls(pos, dimensions, frames, np.asarray(times), masses)
+        kind = type(traj).__name__
+        plain = not getattr(traj, "transformations", ())
+        if kind == "DCDReader" and plain and getattr(traj, "convert_units", True) is not None:
+            from .coordinates.dcd import DCDFile, _dims_from_unitcell, AKMA_TO_PS
+            with DCDFile(traj.filename) as f:
+                if regular is not None:
+                    r = range(*regular.indices(f.n_frames))
+                    xyz, cell = f.readframes(r.start, r.stop, r.step, indices=None if whole else aidx)
+                else:
+                    from .coordinates.dcd import _host_buffer
+                    xyz = _host_buffer((len(fidx), len(aidx), 3), True)
+                    cell = np.zeros((len(fidx), 6))
+                    for k, fr in enumerate(fidx):          # arbitrary frame lists: one read each
+                        f.readframes(int(fr), int(fr) + 1, 1, indices=None if whole else aidx, out=xyz[k:k + 1])
+                        cell[k] = f.readframes(int(fr), int(fr) + 1, 1, indices=aidx[:1])[1][0]
+                h = f.header
+            dims = _dims_from_unitcell(cell) if h["is_periodic"] else None
+            if dims is not None and not np.any(dims):
+                dims = None
+            nsavc = h["nsavc"] if h["nsavc"] else 1
+            times = (fidx + h["istart"] / nsavc) * (h["delta"] * nsavc * AKMA_TO_PS)
+            return cls(xyz, dims, fidx, times, masses)
+        if kind == "MemoryReader" and plain:
+            arr = traj.get_array()
+            order = traj.stored_order
+            pos = np.transpose(arr, (order.find("f"), order.find("a"), order.find("c")))[fidx]
+            if not whole:
+                pos = pos[:, aidx]
+            dims = np.asarray(traj.dimensions_array, dtype=np.float32)[fidx]
+            dims = None if not np.any(dims) else dims
+            return cls(pos, dims, fidx, fidx * float(traj.dt), masses)
+        # generic reader: bulk coordinates, one pass for unit cells and times
+        _READER_LOCK.acquire()
+        cur = traj.ts.frame
+        try:
+            if regular is not None and len(fidx):
+                st = fidx[1] - fidx[0] if len(fidx) > 1 else 1
+                pos = np.asarray(traj.timeseries(atomgroup=atomgroup, start=int(fidx[0]), stop=int(fidx[-1]) + 1,
+                                                 step=int(st), order="fac"))
+                walk = traj[int(fidx[0]):int(fidx[-1]) + 1:int(st)]
+            else:
+                pos = np.empty((len(fidx), len(aidx), 3), dtype=np.float32)
+                walk = traj[fidx] if len(fidx) else []
+            dims, times = [], []
+            for k, ts in enumerate(walk):
+                if regular is None:
+                    pos[k] = atomgroup.positions
+                dims.append(None if ts.dimensions is None else np.array(ts.dimensions, dtype=np.float32))
+                times.append(ts.time)
+        finally:
+            if 0 <= cur < n_all:
+                traj[cur]
+            _READER_LOCK.release()
+        dimensions = None if (not dims or any(d is None for d in dims)) else np.stack(dims)
+        return cls(pos, dimensions, fidx, np.asarray(times), masses)
 
 
 def as_block(x, dimensions=None):
