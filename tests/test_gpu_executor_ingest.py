@@ -78,7 +78,8 @@ def test_executor_rmsd_contacts_aligntraj(mda):
     want = rms.RMSD(u, select="all", weights="mass", groupselections=["index 0:99", "index 400:500"]).run()
     got = rms.RMSD(u, select="all", weights="mass", groupselections=["index 0:99", "index 400:500"])
     got.run(backend=cuda_backend(nw), n_parts=5, unsupported_backend=True)
-    assert np.allclose(got.results.rmsd, want.results.rmsd, rtol=1e-6, atol=1e-9)
+    # frame 0 against itself: both sides return the noise floor of sqrt(2 (E0 - lambda) / N), ~1e-7
+    assert np.allclose(got.results.rmsd, want.results.rmsd, rtol=1e-6, atol=5e-6)
     # Contacts
     sel_a, sel_b = u.atoms[:60], u.atoms[60:140]
     refg = (u.atoms[:60], u.atoms[60:140])
