@@ -211,8 +211,16 @@ class InterRDF(BlockAnalysis):
                     float(self._maxrange), d2_max, use_grid, ptr(thr), nbins, lo, hi, int(xa),
                     int(xb), ptr(counts), HOST, None)
             check(rc)
-        for box in blk.dimensions:                       # rdf.py:291, summed in frame order
-            self.volume_cum += box_volume(box)
+        # rdf.py:291 adds ts.volume frame by frame: the same sequential float64 sum, without a
+        # Python statement per frame (a constant cell needs one box_volume call)
+        if blk.n_frames == 0:
+            vols = np.zeros(0)
+        elif blk.constant_box():
+            vols = np.full(blk.n_frames, box_volume(blk.dimensions[0]), dtype=np.float64)
+        else:
+            vols = np.array([box_volume(b) for b in blk.dimensions], dtype=np.float64)
+        if len(vols):
+            self.volume_cum = float(np.add.accumulate(np.concatenate(([float(self.volume_cum)], vols)))[-1])
         if self._distributed:
             counts = self._allreduce(counts, dev, blk)
         self._device_counts = counts if dev else None
@@ -221,22 +229,31 @@ class InterRDF(BlockAnalysis):
         self._nA, self._nB = na, nb
 
     def _allreduce(self, counts, dev, blk):
-        """Sum histogram, cumulative volume and frame count over all ranks."""
+        """Sum histogram, cumulative volume and frame count over all ranks in ONE collective:
+        ``[count[nbins], volume_cum, n_frames]`` as float64 (counts are integers below 2**53, so
+        their float64 sum is exact -- the reference's own ``count`` array is float64, rdf.py:262)."""
         import torch
         from .. import parallel
         if not parallel.is_distributed():
             return counts
-        if not dev:
-            counts = torch.as_tensor(counts.astype(np.int64))
-            if torch.distributed.get_backend() == "nccl":
-                counts = counts.cuda()
-        meta = torch.tensor([float(self.volume_cum), float(self.n_frames)], dtype=torch.float64,
-                            device=counts.device)
-        parallel.allreduce_sum(counts)
-        parallel.allreduce_sum(meta)
-        self.volume_cum = float(meta[0])
-        self.n_frames = int(round(float(meta[1])))
-        return counts if dev else counts.cpu().numpy().astype(np.uint64)
+        if dev:
+            device = counts.device
+            local = counts
+        else:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.distributed.get_backend() == "nccl" else "cpu"
+            local = torch.as_tensor(counts.astype(np.int64)).to(device)
+        nb = local.shape[0]
+        packed = torch.empty(nb + 2, dtype=torch.float64, device=device)
+        packed[:nb] = local
+        packed[nb:] = torch.tensor([float(self.volume_cum), float(self.n_frames)], dtype=torch.float64)
+        parallel.allreduce_sum(packed)
+        tail = packed[nb:].cpu()
+        if float(packed[:nb].max()) >= 2.0 ** 53:
+            raise OverflowError("histogram counts exceed 2**53: the float64 reduction is not exact")
+        self.volume_cum = float(tail[0])
+        self.n_frames = int(round(float(tail[1])))
+        total = packed[:nb].to(torch.int64)
+        return total if dev else total.cpu().numpy().astype(np.uint64)
 
     def _conclude(self):
         norm = self.n_frames

@@ -68,7 +68,9 @@ class FrameBlock:
         return self.n_atoms
 
     def constant_box(self):
-        return self.dimensions is None or bool((self.dimensions == self.dimensions[0]).all())
+        if self.dimensions is None or self.n_frames == 0:
+            return True
+        return bool((self.dimensions == self.dimensions[0]).all())
 
     def slice_frames(self, sl):
         """Frames ``sl`` (slice or index array) as a new block sharing memory where possible."""

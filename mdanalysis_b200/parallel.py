@@ -91,31 +91,57 @@ class ShardedRun:
         if rank is None:
             rank = _dist().get_rank() if is_distributed() else 0
         lo, hi = shard_bounds(block.n_frames, world_size, rank)
-        local = block.slice_frames(slice(lo, hi))
-        ana = self.make_analysis(local)
-        if hi > lo:
-            ana.run()
-        out = {}
         dev = self.device or ("cuda" if (torch.cuda.is_available() and is_distributed()
                                          and _dist().get_backend() == "nccl") else "cpu")
+        # A rank that fails locally still enters the collectives (the others would wait in
+        # all_reduce / all_gather for ever): the error is agreed on first, then raised everywhere.
+        error = None
+        ana = None
+        try:
+            if hi > lo:
+                local = block.slice_frames(slice(lo, hi))
+                ana = self.make_analysis(local)
+                # "reference = the trajectory itself" means frame ref_frame of the WHOLE run
+                # (analysis/rms.py:560-567), not of this rank's shard
+                if getattr(ana, "_refblock", None) is local:
+                    ana._refblock = block
+                ana.run()
+                shapes = ana.results
+            else:
+                shapes = self._result_shapes(block)
+        except Exception as e:                              # noqa: BLE001 -- re-raised below, on every rank
+            error = e
+        flag = torch.tensor([0.0 if error is None else 1.0], dtype=torch.float64).to(dev)
+        if allreduce_sum(flag).item() > 0:
+            if error is not None:
+                raise error
+            raise RuntimeError("another rank failed in its shard of the run")
+        out = {}
         for name, how in self.reduce.items():
-            val = ana.results.get(name) if hi > lo else None
+            val = np.asarray(shapes[name], dtype=np.float64)
             if how == "sum":
-                ref = val if val is not None else self._empty_like(name, block)
-                t = torch.as_tensor(np.asarray(ref, dtype=np.float64)).to(dev)
+                if hi <= lo:
+                    val = np.zeros_like(val)
+                t = torch.as_tensor(val).to(dev)
                 out[name] = allreduce_sum(t).cpu().numpy()
             elif how == "concat":
-                if val is None:
-                    val = self._empty_like(name, block)[:0]
-                t = torch.as_tensor(np.asarray(val, dtype=np.float64)).to(dev)
+                if hi <= lo:
+                    val = val[:0]
+                t = torch.as_tensor(val).to(dev)
                 out[name] = allgather_series(t, block.n_frames, world_size).cpu().numpy()
             else:
                 raise ValueError(how)
         self.analysis = ana
         return out
 
-    def _empty_like(self, name, block):
-        probe = self.make_analysis(block.slice_frames(slice(0, 0)))
-        probe.n_frames = 0
-        probe._prepare(block.slice_frames(slice(0, 0)))
-        return np.asarray(probe.results[name], dtype=np.float64)
+    def _result_shapes(self, block):
+        """Result arrays of a rank WITHOUT frames (world_size > n_frames): the analysis is prepared
+        on the first frame of the whole block -- never on an empty one, whose ``_prepare`` would
+        index frame 0 -- and only the shapes / dtypes of what it allocates are used."""
+        probe_block = block.slice_frames(slice(0, 1))
+        probe = self.make_analysis(probe_block)
+        if hasattr(probe, "_b2"):
+            probe._b2_run = probe._b2
+        probe.n_frames = probe_block.n_frames
+        probe._prepare(probe_block)
+        return probe.results

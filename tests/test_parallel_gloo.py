@@ -89,6 +89,65 @@ def test_sharded_run_two_ranks(tmp_path, n_frames):
     assert (int(other["lo"]), int(other["hi"])) == ((int(split[1][0]), int(split[1][-1]) + 1) if len(split[1]) else (0, 0))
 
 
+class _RefToy(_ToyAnalysis):
+    """Like RMSD(reference=None): measures against frame 0 of ``_refblock`` (default: its own block)."""
+
+    def __init__(self, block):
+        super().__init__(block)
+        self._refblock = block
+
+    def run(self):
+        blk = self._block
+        self._prepare(blk)
+        ref = self._refblock.positions[0].astype(np.float64)
+        d = np.sqrt(((blk.positions.astype(np.float64) - ref[None]) ** 2).sum(axis=(1, 2)))
+        self.results.series = np.stack([blk.frames.astype(np.float64), d], axis=1)
+        return self
+
+
+class _FailsOnRank1(_ToyAnalysis):
+    def run(self):
+        import torch.distributed as dist
+        if dist.get_rank() == 1:
+            raise ValueError("bad shard")
+        return super().run()
+
+
+def _worker_ref(rank, world, port, out):
+    import torch.distributed as dist
+    from mdanalysis_b200 import FrameBlock, parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        blk = FrameBlock(rng.random((6, 4, 3)).astype(np.float32))
+        res = parallel.ShardedRun(_RefToy, {"series": "concat"}, device="cpu").run(blk)
+        msg = ""
+        try:
+            parallel.ShardedRun(_FailsOnRank1, {"count": "sum"}, device="cpu").run(blk)
+        except Exception as e:                                   # every rank must get here, none may hang
+            msg = f"{type(e).__name__}: {e}"
+        np.savez(out + f".r{rank}.npz", series=res["series"], msg=msg)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_sharded_reference_is_global_and_errors_reach_every_rank(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "ref")
+    mp.spawn(_worker_ref, args=(2, _free_port(), out), nprocs=2, join=True)
+    rng = np.random.default_rng(11)
+    pos = rng.random((6, 4, 3)).astype(np.float64).astype(np.float32).astype(np.float64)
+    want = np.sqrt(((pos - pos[0][None]) ** 2).sum(axis=(1, 2)))
+    for r in range(2):
+        got = np.load(out + f".r{r}.npz")
+        assert np.allclose(got["series"][:, 1], want, rtol=0, atol=1e-12)   # frame 0 of the WHOLE run, on both ranks
+    assert "bad shard" in str(np.load(out + ".r1.npz")["msg"])
+    assert "another rank failed" in str(np.load(out + ".r0.npz")["msg"])
+
+
 @pytest.mark.parametrize("n,world", [(10, 3), (98, 8), (5, 8), (1000, 8), (0, 2)])
 def test_shard_frames_matches_reference_split(n, world):
     from mdanalysis_b200 import parallel
