@@ -8,6 +8,7 @@ nsgrid.FastNS / qcprot.CalcRMSDRotationalMatrix are the GPU twins.  What must ho
 of the module passes except the listed ones, which probe Cython-level behaviour the Python twin
 does not have (documented next to each).  Skipped when baseline/_ref is absent.
 """
+import json
 import os
 import re
 import subprocess
@@ -56,6 +57,17 @@ MODULES = {
                                    "client_Dihedral0": "multiprocessing fork + CUDA"},
 }
 
+# The substrings above only say WHY a family of tests cannot pass here.  WHICH tests may fail is the exact
+# list of pytest ids in tests/golden/reference_allowed_failures.json (recorded on the GPU box with
+# MDAGPU_RECORD_REF_FAILURES=<file>, every id matching one of the reasons above): a new failure whose
+# id merely contains "test_distance_box" or "client_RMSD0" is NOT excused.
+EXACT_FILE = os.path.join(ROOT, "tests", "golden", "reference_allowed_failures.json")
+try:
+    with open(EXACT_FILE) as _fh:
+        EXACT = json.load(_fh)
+except OSError:
+    EXACT = None
+
 
 @pytest.mark.parametrize("module", list(MODULES))
 def test_reference_module_on_cuda_backend(module):
@@ -78,5 +90,17 @@ def test_reference_module_on_cuda_backend(module):
     failed = re.findall(r"^(?:FAILED|ERROR) (\S+)", text, flags=re.M)    # fixture errors count as failures
     allowed = {k: v for k, v in MODULES[module].items() if k != "-k"}
     unexpected = [f for f in failed if not any(a in f for a in allowed)]
+    record = os.environ.get("MDAGPU_RECORD_REF_FAILURES")
+    if record:
+        seen = {}
+        if os.path.exists(record):
+            with open(record) as fh:
+                seen = json.load(fh)
+        seen[module] = {f: next(v for a, v in allowed.items() if a in f) for f in sorted(failed)
+                        if any(a in f for a in allowed)}
+        with open(record, "w") as fh:
+            json.dump(seen, fh, indent=1, sort_keys=True)
+    elif EXACT is not None:
+        unexpected = [f for f in failed if f not in EXACT.get(module, {})]
     assert not unexpected, f"{len(unexpected)} unexpected failures, e.g. {unexpected[:5]}\n{tail}"
     print(f"{module}: {m.group(1)} passed, {len(failed)} allowed failures, {launches.group(1)} kernel launches")
