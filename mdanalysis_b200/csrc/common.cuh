@@ -77,6 +77,13 @@ struct DevBuf {
     template <class T> T *as() const { return (T *)p; }
 };
 
+// Transfers of caller-owned host memory (hostcopy.cu): pageable memory goes through a pinned
+// ring with the host-side copies on a small thread pool, pinned memory straight to the DMA.
+// host_to_device returns once `host` has been read; device_to_host once `host` holds the data.
+bool host_is_pinned(const void *p);
+cudaError_t host_to_device(void *dev, const void *host, size_t bytes, cudaStream_t st);
+cudaError_t device_to_host(void *host, const void *dev, size_t bytes, cudaStream_t st);
+
 // Input that may live on the host (space == MDAGPU_HOST: staged through a
 // stream-ordered device buffer) or already on the device (used in place).
 struct StagedIn {
@@ -89,7 +96,7 @@ struct StagedIn {
         if (e != cudaSuccess) return e;
         dev = buf.p;
         if (bytes == 0) return cudaSuccess;
-        return cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st);
+        return host_to_device(buf.p, src, bytes, st);
     }
     template <class T> const T *as() const { return (const T *)dev; }
 };
@@ -111,15 +118,13 @@ struct StagedOut {
         cudaError_t e = buf.alloc(n, st);
         if (e != cudaSuccess) return e;
         dev = buf.p;
-        if (copy_in && n) return cudaMemcpyAsync(dev, host, n, cudaMemcpyHostToDevice, st);
+        if (copy_in && n) return host_to_device(dev, host, n, st);
         return cudaSuccess;
     }
     cudaError_t finish()
     {
         if (!host || !bytes) return cudaSuccess;
-        cudaError_t e = cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) return e;
-        return cudaStreamSynchronize(s);
+        return device_to_host(host, dev, bytes, s);
     }
     template <class T> T *as() const { return (T *)dev; }
 };

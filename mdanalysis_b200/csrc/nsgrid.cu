@@ -528,10 +528,14 @@ extern "C" int mdagpu_pairs_export(const mdagpu_pairs *p, int64_t *pairs, double
     cudaStream_t st = (cudaStream_t)stream;
     MDA_REQUIRE(p != nullptr, "mdagpu_pairs_export: NULL pairs");
     if (p->count == 0) return MDAGPU_OK;
-    const cudaMemcpyKind kind = space == MDAGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    if (pairs) MDA_CUDA(cudaMemcpyAsync(pairs, p->pairs, p->count * 2 * sizeof(int64_t), kind, st));
-    if (distances) MDA_CUDA(cudaMemcpyAsync(distances, p->dist, p->count * sizeof(double), kind, st));
-    if (space != MDAGPU_DEVICE) MDA_CUDA(cudaStreamSynchronize(st));
+    if (space == MDAGPU_DEVICE) {
+        if (pairs) MDA_CUDA(cudaMemcpyAsync(pairs, p->pairs, p->count * 2 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        if (distances) MDA_CUDA(cudaMemcpyAsync(distances, p->dist, p->count * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        return MDAGPU_OK;
+    }
+    // the host arrays are NumPy's (pageable): staged through the pinned ring (hostcopy.cu)
+    if (pairs) MDA_CUDA(device_to_host(pairs, p->pairs, p->count * 2 * sizeof(int64_t), st));
+    if (distances) MDA_CUDA(device_to_host(distances, p->dist, p->count * sizeof(double), st));
     return MDAGPU_OK;
 }
 

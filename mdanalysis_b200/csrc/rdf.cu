@@ -453,14 +453,28 @@ struct HostPipe {
         }
         return e;
     }
+    // Pinned frames: the DMA is queued at once and runs under the kernels of the piece before.
+    // Pageable frames are staged by host threads (hostcopy.cu), which blocks this thread: that
+    // upload is deferred until the kernels of the current piece have been launched (release()).
+    bool deferred = false;
+    uint64_t d_piece = 0, d_f0 = 0, d_fc = 0;
     cudaError_t upload(uint64_t piece_no, uint64_t f0, uint64_t fc)
+    {
+        if (piece_no > 0 && !(host_is_pinned(A + f0 * na * 3) && (!B || host_is_pinned(B + f0 * nb * 3)))) {
+            deferred = true;
+            d_piece = piece_no; d_f0 = f0; d_fc = fc;
+            return cudaSuccess;
+        }
+        return upload_now(piece_no, f0, fc);
+    }
+    cudaError_t upload_now(uint64_t piece_no, uint64_t f0, uint64_t fc)
     {
         const int k = (int)(piece_no & 1);
         cudaError_t e = cudaStreamWaitEvent(copy, freed[k], 0);
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(abuf[k].p, A + f0 * na * 3, fc * na * 3 * sizeof(float), cudaMemcpyHostToDevice, copy);
+            e = host_to_device(abuf[k].p, A + f0 * na * 3, fc * na * 3 * sizeof(float), copy);
         if (e == cudaSuccess && B)
-            e = cudaMemcpyAsync(bbuf[k].p, B + f0 * nb * 3, fc * nb * 3 * sizeof(float), cudaMemcpyHostToDevice, copy);
+            e = host_to_device(bbuf[k].p, B + f0 * nb * 3, fc * nb * 3 * sizeof(float), copy);
         if (e == cudaSuccess) e = cudaEventRecord(ready[k], copy);
         return e;
     }
@@ -471,7 +485,15 @@ struct HostPipe {
         *b = B ? bbuf[k].as<float>() : nullptr;
         return cudaStreamWaitEvent(compute, ready[k], 0);
     }
-    cudaError_t release(uint64_t piece_no) { return cudaEventRecord(freed[(int)(piece_no & 1)], compute); }
+    cudaError_t release(uint64_t piece_no)
+    {
+        cudaError_t e = cudaEventRecord(freed[(int)(piece_no & 1)], compute);
+        if (e == cudaSuccess && deferred) {
+            deferred = false;
+            e = upload_now(d_piece, d_f0, d_fc);
+        }
+        return e;
+    }
 };
 
 }  // namespace mdagpu
