@@ -180,6 +180,15 @@ MDAGPU_API int mdagpu_capped_bruteforce(const float *ref, uint64_t n, const floa
 MDAGPU_API int mdagpu_qcp(const double *ref, const double *conf, uint64_t n, double *rot,
                const double *weights, double *rmsd, int space, mdagpu_stream_t stream);
 
+/* The two public halves of the above (lib/qcprot.pyx:179-277 InnerProduct, :326-543
+ * FastCalcRMSDAndRotation), for callers that use them separately:
+ *   inner_product: A[9] = sum_i w_i coords1_i (x) coords2_i (row = component of coords1),
+ *                  *E0 = (sum w |coords1|^2 + sum w |coords2|^2) / 2; float64 [n,3] inputs
+ *   solve:         RMSD (and rot[9], unless NULL) from A, E0 and the atom count n; host pointers */
+MDAGPU_API int mdagpu_qcp_inner_product(const double *coords1, const double *coords2, uint64_t n,
+               const double *weights, double *A, double *E0, int space, mdagpu_stream_t stream);
+MDAGPU_API int mdagpu_qcp_solve(const double *A, double E0, double n, double *rot, double *rmsd);
+
 /* Batched driver for analysis.rms.RMSD._single_frame (rms.py:685-727) and
  * analysis.align.AlignTraj._single_frame / _fit_to (align.py:310-366, 843-854).
  *   traj      float32 [F, natoms, 3]
@@ -281,6 +290,23 @@ MDAGPU_API int mdagpu_contacts_self(const float *xyz, uint64_t n, uint64_t nfram
                          mdagpu_stream_t stream);
 
 /* ---- trajectory ingest: the step in front of the path ---- */
+
+/* ---- reductions that follow the hot kernels inside the analyses (csrc/reduce.cu) ----
+ * frame_mean:       mean[nsel,3] (float64) = mean over the frames of traj[f, sel] -- AverageStructure
+ *                   (analysis/align.py:1072-1083); sel = NULL: the first nsel atoms
+ * group_rmsd:       out[f] = sqrt(sum_i w_i |traj[f, idx_i] - ref_i|^2 / g) -- RMSD groupselections
+ *                   (analysis/rms.py:716-721); weights already divided by their mean, or NULL
+ * contact_fraction: out[f] = fraction of native contacts of frame f from its pair distances r[f, :]
+ *                   method 0 hard_cut_q (r <= r0), 1 radius_cut_q (r <= radius),
+ *                   2 soft_cut_q 1 / (1 + exp(beta (r - lambda r0))) -- analysis/contacts.py:231-312 */
+MDAGPU_API int mdagpu_frame_mean(const float *traj, uint64_t nframes, uint64_t natoms, const int32_t *sel,
+               uint64_t nsel, double *mean, int space, mdagpu_stream_t stream);
+MDAGPU_API int mdagpu_group_rmsd(const float *traj, uint64_t nframes, uint64_t natoms, const int32_t *idx,
+               uint64_t g, const double *ref, const double *weights, double *out, int space,
+               mdagpu_stream_t stream);
+MDAGPU_API int mdagpu_contact_fraction(const double *r, uint64_t nframes, uint64_t npairs, const double *r0,
+               int method, double radius, double beta, double lambda, double *out, int space,
+               mdagpu_stream_t stream);
 
 /* Bulk DCD reader: coordinates/DCD.py:279-344 (DCDReader.timeseries) ->
  * lib/formats/libdcd.pyx:583-700 (DCDFile.readframes), C side lib/formats/include/readdcd.h.

@@ -52,6 +52,8 @@ SIGNATURES = {
     "mdagpu_pairs_free": (None, [_vp]),
     "mdagpu_capped_bruteforce": (_i, [_vp, _u64, _vp, _u64, _d, _d, _i, _vp, _i, _vp, C.POINTER(_vp)]),
     "mdagpu_qcp": (_i, [_vp, _vp, _u64, _vp, _vp, C.POINTER(_d), _i, _vp]),
+    "mdagpu_qcp_inner_product": (_i, [_vp, _vp, _u64, _vp, _vp, C.POINTER(_d), _i, _vp]),
+    "mdagpu_qcp_solve": (_i, [_vp, _d, _d, _vp, C.POINTER(_d)]),
     "mdagpu_qcp_trajectory": (_i, [_vp, _u64, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mdagpu_pairwise_rmsd": (_i, [_vp, _u64, _u64, _vp, _u64, _vp, _i, _d, _vp, _i, _vp]),
     "mdagpu_rdf_accumulate": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,
@@ -61,6 +63,9 @@ SIGNATURES = {
     "mdagpu_rdf_sites_accumulate": (_i, [_vp, _u64, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _i,
                                          _d, _d, _vp, _i, _vp]),
     "mdagpu_contacts_self": (_i, [_vp, _u64, _u64, _i, _vp, _d, _d, _vp, _vp, _i, _vp]),
+    "mdagpu_frame_mean": (_i, [_vp, _u64, _u64, _vp, _u64, _vp, _i, _vp]),
+    "mdagpu_group_rmsd": (_i, [_vp, _u64, _u64, _vp, _u64, _vp, _vp, _vp, _i, _vp]),
+    "mdagpu_contact_fraction": (_i, [_vp, _u64, _u64, _vp, _i, _d, _d, _d, _vp, _i, _vp]),
     "mdagpu_dcd_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "mdagpu_dcd_close": (None, [_vp]),
     "mdagpu_dcd_header": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(_i), C.POINTER(C.c_int32),
@@ -142,7 +147,20 @@ def tensor_ptr(t):
 
 
 def current_stream(t=None):
-    """cudaStream_t of torch's current stream on the tensor's device."""
+    """cudaStream_t of torch's current stream on the tensor's device.  Every device-resident entry
+    point fetches its stream here right before the call, so this is also where the tensor's device
+    is made current for the library (scratch allocations, SM count and launches follow the
+    current device; a tensor on cuda:1 while cuda:0 is current would otherwise be served by the
+    wrong one)."""
     import torch
     dev = t.device if t is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        torch.cuda.set_device(dev)
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def same_device(*tensors):
+    """ValueError unless all given tensors (None skipped) live on one CUDA device."""
+    devs = {t.device for t in tensors if t is not None and is_tensor(t)}
+    if len(devs) > 1:
+        raise ValueError(f"all tensor arguments must be on the same device, got {sorted(map(str, devs))}")

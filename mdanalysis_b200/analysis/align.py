@@ -3,7 +3,7 @@
 """
 import numpy as np
 
-from .._cabi import is_tensor
+from .._cabi import DEVICE, check, current_stream, is_tensor, load, tensor_ptr
 from ..frames import as_block
 from ..lib import qcprot as qcp
 from .base import BlockAnalysis
@@ -143,6 +143,12 @@ class AverageStructure(BlockAnalysis):
                 blk.positions[...] = moved.cpu().numpy()
             else:
                 blk.positions = moved
-        sel = moved if self._sel_m is None else moved[:, torch.as_tensor(self._sel_m, device=moved.device)]
-        self.results.positions = sel.to(torch.float64).mean(dim=0).cpu().numpy()
-        self.results.rmsd = float(vals.to(torch.float64).mean())
+        # float64 mean over the frames of the fitted atoms: mdagpu_frame_mean (csrc/reduce.cu)
+        sel = None if self._sel_m is None else torch.as_tensor(np.ascontiguousarray(self._sel_m, dtype=np.int32),
+                                                               device=moved.device)
+        nsel = moved.shape[1] if sel is None else int(sel.shape[0])
+        mean = torch.empty((nsel, 3), dtype=torch.float64, device=moved.device)
+        check(load().mdagpu_frame_mean(tensor_ptr(moved), moved.shape[0], moved.shape[1], tensor_ptr(sel), nsel,
+                                       tensor_ptr(mean), DEVICE, current_stream(moved)))
+        self.results.positions = mean.cpu().numpy()
+        self.results.rmsd = float(vals.sum().item() / vals.shape[0])

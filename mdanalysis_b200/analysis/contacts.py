@@ -188,20 +188,37 @@ class Contacts(BlockAnalysis):
     def _compute(self, blk):
         ts = self.results.timeseries
         ts[:, 0] = blk.frames
+        # the native-pair distances stay on the device; only q[F] comes back (csrc/reduce.cu).  A
+        # user-supplied callable (or extra kwargs) is evaluated on the host, frame by frame, as in
+        # the reference (contacts.py:486-499).
+        import torch
+        dev = blk.positions.device if blk.on_device else torch.device("cuda", torch.cuda.current_device())
         A = blk.select(self._idx[0]).positions
         B = blk.select(self._idx[1]).positions
+        if not blk.on_device:
+            A, B = torch.as_tensor(A).to(dev), torch.as_tensor(B).to(dev)
         dims = blk.dimensions if self.pbc else None
+        kw = self.fraction_kwargs
+        builtin = {"hard_cut": 0, "radius_cut": 1, "soft_cut": 2}.get(self._method_name)
+        if builtin == 2:
+            if set(kw) - {"beta", "lambda_constant"}:
+                builtin = None
+        elif builtin is not None and kw:
+            builtin = None
         for k, (mask, r0) in enumerate(zip(self.initial_contacts, self.r0), 1):
             ii, jj = np.nonzero(mask)                    # row-major, the order of d[mask]
             r = pair_list_distances(A, B, ii, jj, dims)
-            if is_tensor(r):
-                r = r.detach().cpu().numpy()
-            r0s = r0[mask]
+            r0s = np.ascontiguousarray(r0[mask], dtype=np.float64)
+            if builtin is not None and r0s.size:
+                q = torch.empty((blk.n_frames,), dtype=torch.float64, device=dev)
+                r0d = torch.as_tensor(r0s, device=dev)
+                check(load().mdagpu_contact_fraction(tensor_ptr(r), blk.n_frames, r0s.size, tensor_ptr(r0d), builtin,
+                                                     float(self.radius), float(kw.get("beta", 5.0)),
+                                                     float(kw.get("lambda_constant", 1.8)), tensor_ptr(q), DEVICE,
+                                                     current_stream(r)))
+                ts[:, k] = q.cpu().numpy()
+                continue
+            r = r.detach().cpu().numpy()
             with np.errstate(invalid="ignore", divide="ignore"):
-                if self._method_name == "hard_cut" and not self.fraction_kwargs:
-                    ts[:, k] = (r <= r0s[None]).sum(axis=1) / r0s.size
-                elif self._method_name == "radius_cut" and not self.fraction_kwargs:
-                    ts[:, k] = (r <= self.radius).sum(axis=1) / r0s.size
-                else:
-                    for f in range(blk.n_frames):
-                        ts[f, k] = self.fraction_contacts(r[f], r0s, **self.fraction_kwargs)
+                for f in range(blk.n_frames):
+                    ts[f, k] = self.fraction_contacts(r[f], r0s, **self.fraction_kwargs)

@@ -12,7 +12,7 @@ is resolved through ``select_atoms``.
 """
 import numpy as np
 
-from .._cabi import is_tensor
+from .._cabi import DEVICE, check, current_stream, is_tensor, load, tensor_ptr
 from ..frames import FrameBlock, as_block
 from ..lib import qcprot as qcp
 from .base import BlockAnalysis
@@ -173,10 +173,15 @@ class RMSD(BlockAnalysis):
             gw = wg[k]
             if isinstance(gw, str) and gw == "mass":
                 gw = blk.masses[gm]
-            refpos = torch.as_tensor(self._ref_all[gr].astype(np.float64), device=moved.device)
-            sel = moved[:, torch.as_tensor(np.asarray(gm), device=moved.device)].to(torch.float64)
-            diff2 = (sel - refpos[None]) ** 2
+            # plain RMSD of the group on the superposed frames, one CTA per frame (csrc/reduce.cu)
+            refpos = torch.as_tensor(np.ascontiguousarray(self._ref_all[gr], dtype=np.float64), device=moved.device)
+            idx = torch.as_tensor(np.ascontiguousarray(gm, dtype=np.int32), device=moved.device)
+            w_d = None
             if gw is not None:
-                gw = np.asarray(gw, dtype=np.float64) / np.mean(gw)
-                diff2 = diff2 * torch.as_tensor(gw, device=moved.device)[None, :, None]
-            out[:, 3 + k] = torch.sqrt(diff2.sum(dim=(1, 2)) / len(gm)).cpu().numpy()
+                gw = np.asarray(gw, dtype=np.float64)
+                w_d = torch.as_tensor(np.ascontiguousarray(gw / np.mean(gw)), device=moved.device)
+            vals_g = torch.empty((moved.shape[0],), dtype=torch.float64, device=moved.device)
+            check(load().mdagpu_group_rmsd(tensor_ptr(moved), moved.shape[0], moved.shape[1], tensor_ptr(idx), len(gm),
+                                           tensor_ptr(refpos), tensor_ptr(w_d), tensor_ptr(vals_g), DEVICE,
+                                           current_stream(moved)))
+            out[:, 3 + k] = vals_g.cpu().numpy()

@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
 // single pair of already-centred float64 structures (CalcRMSDRotationalMatrix)
 __global__ void __launch_bounds__(QCP_THREADS)
 qcp_single_kernel(const double *__restrict__ ref, const double *__restrict__ conf, uint64_t n,
-                  const double *__restrict__ w, double *__restrict__ rot, double *__restrict__ rmsd)
+                  const double *__restrict__ w, double *__restrict__ rot, double *__restrict__ rmsd,
+                  int inner_only)
 {
     __shared__ double scratch[11 * (QCP_THREADS / 32)];
     double acc[11];
@@ -598,12 +599,28 @@ qcp_single_kernel(const double *__restrict__ ref, const double *__restrict__ con
     }
     block_sum<11, QCP_THREADS>(acc, scratch);
     if (threadIdx.x == 0) {
-        double R[9];
         const double E0 = (acc[9] + acc[10]) * 0.5;
+        if (inner_only) {                                // InnerProduct (qcprot.pyx:179-277): A[9] and E0
+            for (int k = 0; k < 9; ++k) rot[k] = acc[k];
+            *rmsd = E0;
+            return;
+        }
+        double R[9];
         *rmsd = qcp_solve(rot ? R : nullptr, acc, E0, (double)n);
         if (rot)
             for (int k = 0; k < 9; ++k) rot[k] = R[k];
     }
+}
+
+// FastCalcRMSDAndRotation (qcprot.pyx:326-543) on its own: the quartic, Newton, the quaternion
+__global__ void qcp_solve_kernel(const double *__restrict__ A, double E0, double n, double *__restrict__ rot,
+                                 double *__restrict__ rmsd)
+{
+    double a[9], R[9];
+    for (int k = 0; k < 9; ++k) a[k] = A[k];
+    *rmsd = qcp_solve(rot ? R : nullptr, a, E0, n);
+    if (rot)
+        for (int k = 0; k < 9; ++k) rot[k] = R[k];
 }
 
 }  // namespace mdagpu
@@ -625,7 +642,50 @@ extern "C" int mdagpu_qcp(const double *ref, const double *conf, uint64_t n, dou
     MDA_CUDA(ro.init(rot, 9 * sizeof(double), space, st));
     MDA_CUDA(val.alloc(sizeof(double), st));
     MDA_LAUNCH(qcp_single_kernel, 1, QCP_THREADS, 0, st, r.as<double>(), c.as<double>(), n,
-               weights ? w.as<double>() : nullptr, rot ? ro.as<double>() : nullptr, val.as<double>());
+               weights ? w.as<double>() : nullptr, rot ? ro.as<double>() : nullptr, val.as<double>(), 0);
+    MDA_CHECK_LAUNCH();
+    MDA_CUDA(cudaMemcpyAsync(rmsd, val.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (rot) MDA_CUDA(ro.finish());
+    MDA_CUDA(cudaStreamSynchronize(st));
+    return MDAGPU_OK;
+}
+
+extern "C" int mdagpu_qcp_inner_product(const double *coords1, const double *coords2, uint64_t n,
+                                        const double *weights, double *A, double *E0, int space,
+                                        mdagpu_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    MDA_REQUIRE(coords1 && coords2 && A && E0, "mdagpu_qcp_inner_product: NULL argument");
+    MDA_REQUIRE(n > 0, "mdagpu_qcp_inner_product: empty structures");
+    StagedIn c1, c2, w;
+    StagedOut a;
+    DevBuf val;
+    MDA_CUDA(c1.init(coords1, n * 3 * sizeof(double), space, st));
+    MDA_CUDA(c2.init(coords2, n * 3 * sizeof(double), space, st));
+    MDA_CUDA(w.init(weights, n * sizeof(double), space, st));
+    MDA_CUDA(a.init(A, 9 * sizeof(double), space, st));
+    MDA_CUDA(val.alloc(sizeof(double), st));
+    // the kernel's first structure is coords2 ("ref"), its second coords1 ("conf"): A's rows follow coords1
+    MDA_LAUNCH(qcp_single_kernel, 1, QCP_THREADS, 0, st, c2.as<double>(), c1.as<double>(), n,
+               weights ? w.as<double>() : nullptr, a.as<double>(), val.as<double>(), 1);
+    MDA_CHECK_LAUNCH();
+    MDA_CUDA(cudaMemcpyAsync(E0, val.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    MDA_CUDA(a.finish());
+    MDA_CUDA(cudaStreamSynchronize(st));
+    return MDAGPU_OK;
+}
+
+extern "C" int mdagpu_qcp_solve(const double *A, double E0, double n, double *rot, double *rmsd)
+{
+    MDA_REQUIRE(A && rmsd, "mdagpu_qcp_solve: NULL argument");
+    cudaStream_t st = nullptr;
+    StagedIn a;
+    StagedOut ro;
+    DevBuf val;
+    MDA_CUDA(a.init(A, 9 * sizeof(double), MDAGPU_HOST, st));
+    MDA_CUDA(ro.init(rot, 9 * sizeof(double), MDAGPU_HOST, st));
+    MDA_CUDA(val.alloc(sizeof(double), st));
+    MDA_LAUNCH(qcp_solve_kernel, 1, 1, 0, st, a.as<double>(), E0, n, rot ? ro.as<double>() : nullptr, val.as<double>());
     MDA_CHECK_LAUNCH();
     MDA_CUDA(cudaMemcpyAsync(rmsd, val.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     if (rot) MDA_CUDA(ro.finish());

@@ -38,6 +38,42 @@ def CalcRMSDRotationalMatrix(ref, conf, N, rot, weights):
     return float(val.value)
 
 
+def InnerProduct(A, coords1, coords2, N, weight):
+    """``A[9]`` (filled in place) ``= sum_i w_i coords1_i (x) coords2_i`` and the return value
+    ``E0 = (sum w |coords1|^2 + sum w |coords2|^2) / 2`` -- qcprot.pyx:179-277.  The first ``N``
+    atoms of the two centred ``(n, 3)`` structures are used; float32 or float64 like the
+    reference (accumulated in float64 on the GPU)."""
+    if A is None or coords1 is None or coords2 is None:
+        raise TypeError("Argument 'A'/'coords1'/'coords2' must not be None")
+    N = int(N)
+    c1 = np.ascontiguousarray(np.asarray(coords1)[:N], dtype=np.float64)
+    c2 = np.ascontiguousarray(np.asarray(coords2)[:N], dtype=np.float64)
+    if c1.ndim != 2 or c2.ndim != 2:
+        raise ValueError("Buffer has wrong number of dimensions (expected 2)")
+    w = None if weight is None else np.ascontiguousarray(np.asarray(weight)[:N], dtype=np.float64)
+    a = np.zeros(9, dtype=np.float64)
+    e0 = C.c_double(0.0)
+    check(load().mdagpu_qcp_inner_product(ptr(c1), ptr(c2), N, ptr(w), ptr(a), C.byref(e0), HOST, None))
+    A[:] = a
+    return float(e0.value)
+
+
+def FastCalcRMSDAndRotation(rot, A, E0, N):
+    """RMSD (returned) and rotation matrix (``rot[9]`` filled in place unless ``None``) from the
+    inner-product matrix ``A[9]``, ``E0`` and the atom count -- qcprot.pyx:326-543."""
+    if A is None:
+        raise TypeError("Argument 'A' must not be None")
+    a = np.ascontiguousarray(A, dtype=np.float64).reshape(-1)
+    if a.shape != (9,):
+        raise ValueError("A must have 9 elements")
+    r = None if rot is None else np.zeros(9, dtype=np.float64)
+    val = C.c_double(0.0)
+    check(load().mdagpu_qcp_solve(ptr(a), float(E0), float(N), ptr(r), C.byref(val)))
+    if rot is not None:
+        rot[:] = r
+    return float(val.value)
+
+
 def qcp_trajectory(traj, reference, select=None, weights=None, want_rotation=False,
                    align=False, convention=0, allclose_shortcut=False, out=None):
     """Per-frame centring + QCP for a whole trajectory block in one launch.

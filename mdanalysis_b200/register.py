@@ -47,6 +47,8 @@ def install(patch_capped: bool = False, masquerade=None, capped_default: str = "
         from .lib import qcprot as gpu_qcprot
         mda_nsgrid.FastNS = gpu_nsgrid.FastNS
         mda_qcprot.CalcRMSDRotationalMatrix = gpu_qcprot.CalcRMSDRotationalMatrix
+        mda_qcprot.InnerProduct = gpu_qcprot.InnerProduct
+        mda_qcprot.FastCalcRMSDAndRotation = gpu_qcprot.FastCalcRMSDAndRotation
     if patch_analysis:
         import MDAnalysis.analysis.diffusionmap as mda_dmap
         from .adapters import run_on_gpu

@@ -51,6 +51,35 @@ def test_qcprot_known_answers():
         assert np.allclose(rot.reshape(3, 3), np.eye(3))
 
 
+def test_inner_product_and_fast_calc_twins(oracle):
+    """The two public halves of qcprot (InnerProduct :179, FastCalcRMSDAndRotation :326) compose to
+    CalcRMSDRotationalMatrix: test_qcprot.py:49-67 (test_regression) drives them this way."""
+    from mdanalysis_b200.lib import qcprot
+    rng = np.random.default_rng(12)
+    n = 777
+    x = rng.normal(0, 10, (n, 3))
+    y = x @ np.linalg.qr(rng.normal(size=(3, 3)))[0] + rng.normal(0, 1, (n, 3))
+    x, y = x - x.mean(0), y - y.mean(0)
+    w = rng.uniform(1, 16, n)
+    for ww in (None, w):
+        A = np.zeros(9)
+        E0 = qcprot.InnerProduct(A, y, x, n, ww)                    # CalcRMSDRotationalMatrix: InnerProduct(A, conf, ref, ...)
+        wcol = np.ones(n) if ww is None else ww
+        assert np.allclose(A.reshape(3, 3), (wcol[:, None] * y).T @ x, rtol=1e-12, atol=1e-9)
+        assert E0 == pytest.approx(0.5 * ((wcol[:, None] * y * y).sum() + (wcol[:, None] * x * x).sum()), rel=1e-12)
+        rot = np.zeros(9)
+        rmsd = qcprot.FastCalcRMSDAndRotation(rot, A, E0, n)
+        rot2 = np.zeros(9)
+        want = oracle.CalcRMSDRotationalMatrix(x, y, n, rot2, ww)
+        assert rmsd == pytest.approx(want, rel=1e-10) and np.allclose(rot, rot2, atol=1e-9)
+        assert qcprot.FastCalcRMSDAndRotation(None, A, E0, n) == pytest.approx(want, rel=1e-10)
+    # first N atoms only, float32 input (the reference's fused type)
+    A32 = np.zeros(9)
+    e = qcprot.InnerProduct(A32, y.astype(np.float32), x.astype(np.float32), 100, None)
+    y3, x3 = y[:100].astype(np.float32).astype(np.float64), x[:100].astype(np.float32).astype(np.float64)
+    assert np.allclose(A32.reshape(3, 3), y3.T @ x3, rtol=1e-10) and e == pytest.approx(0.5 * ((y3 * y3).sum() + (x3 * x3).sum()))
+
+
 def test_rmsd_function(oracle):
     from mdanalysis_b200.analysis.rms import rmsd
     rng = np.random.default_rng(2)
