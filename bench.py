@@ -1010,6 +1010,80 @@ def cpu_baseline_c5(x, obox):
 
 
 # ---------------------------------------------------------------------------------------
+# section 8f rank 1: batched ingest -- analyses on real MDAnalysis universes (DCD file, MemoryReader)
+# ---------------------------------------------------------------------------------------
+def bench_ingest(ctx):
+    """run_on_gpu(<reference analysis object>) end to end: the reader -> FrameBlock ingest
+    (native bulk DCD reader / zero-copy MemoryReader view), staged upload, kernel, results written
+    into the reference object.  Needs the reference as the HOST framework (baseline/_ref)."""
+    torch = ctx.torch
+    ref = real_reference()
+    if ref is None or ctx.rank != 0:
+        return {"skipped": "baseline/_ref (MDAnalysis as the host framework) absent, or not rank 0"}
+    mda = ref[0]
+    from MDAnalysis.analysis import rms
+    from mdanalysis_b200 import FrameBlock, _cabi, run_on_gpu
+    from mdanalysis_b200.analysis.rms import RMSD
+    out = {}
+    data = os.path.join(ROOT, "baseline", "_ref", "MDAnalysisTests", "data")
+    psf, dcd = os.path.join(data, "adk.psf"), os.path.join(data, "adk_dims.dcd")
+    if os.path.exists(dcd):
+        u = mda.Universe(psf, dcd)
+        run_on_gpu(rms.RMSD(u, select="name CA"))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            got = run_on_gpu(rms.RMSD(u, select="name CA"))
+        t_gpu = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        blk = FrameBlock.from_atomgroup(u.select_atoms("name CA"))
+        t_ing = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        want = rms.RMSD(u, select="name CA").run()
+        t_ref = time.perf_counter() - t0
+        out["dcd_adk_rmsd_ca"] = {"frames": len(u.trajectory), "atoms_read": blk.n_atoms, "gpu_call_ms": t_gpu * 1e3,
+                                  "frames_per_s": len(u.trajectory) / t_gpu, "ingest_ms": t_ing * 1e3,
+                                  "reference_ms": t_ref * 1e3, "reference_frames_per_s": len(u.trajectory) / t_ref,
+                                  "max_abs_diff": float(np.abs(got.results.rmsd - want.results.rmsd).max()),
+                                  "api": "run_on_gpu(MDAnalysis.analysis.rms.RMSD(Universe(adk.psf, adk_dims.dcd), select='name CA')): "
+                                         "mdagpu_dcd_readframes (only the 214 CA atoms of the 98 frames) -> QCP kernel"}
+    # a 50k-frame in-memory universe: the ingest must be a view, the upload staged, Python small
+    na, F = 10000, (50000 if not ctx.quick else 4000)
+    ref_np, traj = c4_trajectory(ctx, F, na, SEED0 + 3)
+    arr = _cabi.download(traj)
+    del traj
+    torch.cuda.empty_cache()
+    masses = np.random.default_rng(SEED0 + 3).uniform(1, 32, na)
+
+    def universe(xyz):
+        uu = mda.Universe.empty(na, trajectory=True)
+        uu.add_TopologyAttr("masses", masses)
+        uu.load_new(xyz, order="fac")
+        return uu
+
+    u, ru = universe(arr), universe(ref_np[None].copy())
+    shares = u.trajectory.get_array() is arr or np.shares_memory(u.trajectory.get_array(), arr)
+    run_on_gpu(rms.RMSD(u, ru, select="all"), stop=64)
+    t0 = time.perf_counter()
+    got = run_on_gpu(rms.RMSD(u, ru, select="all"))
+    t_all = time.perf_counter() - t0
+    blk = FrameBlock(arr)
+    RMSD(blk, ref_np).run()
+    t0 = time.perf_counter()
+    core = RMSD(blk, ref_np).run()
+    t_core = time.perf_counter() - t0
+    out["memoryreader_rmsd"] = {
+        "frames": F, "atoms": na, "host_bytes": int(arr.nbytes), "universe_shares_the_array": bool(shares),
+        "run_on_gpu_ms": t_all * 1e3, "frames_per_s": F / t_all, "gb_per_s_from_host": arr.nbytes / t_all / 1e9,
+        "block_call_ms": t_core * 1e3, "overhead_outside_block_call": (t_all - t_core) / t_all,
+        "identical_to_block_call": bool(np.array_equal(got.results.rmsd[:, 2], core.results.rmsd[:, 2])),
+        "api": "run_on_gpu(MDAnalysis.analysis.rms.RMSD(u, ref_u, select='all')) on a MemoryReader universe (pageable "
+               "ndarray): zero-copy ingest, staged H2D (csrc/hostcopy.cu), QCP kernel, results into the reference object; "
+               "block_call = analysis.rms.RMSD(FrameBlock(ndarray), ref).run() on the same array"}
+    del arr, blk, u
+    return out
+
+
+# ---------------------------------------------------------------------------------------
 # section 8f extras kept from round 1: all-pairs RMSD matrix
 # ---------------------------------------------------------------------------------------
 def bench_pairwise(ctx):
@@ -1050,9 +1124,10 @@ def run_ours(args, rank, world, local_rank):
         wanted = [c.strip().upper() for c in args.configs.split(",")]
         table = (("C1", "C1_distance_arrays_adk", bench_c1), ("C2T", "C2_triclinic_interrdf", bench_c2_triclinic),
                  ("C3", "C3_fastns_1M", bench_c3), ("C4", "C4_rmsd_aligntraj", bench_c4),
-                 ("C5", "C5_contacts_100k", bench_c5), ("PW", "pairwise_rmsd_matrix", bench_pairwise))
+                 ("C5", "C5_contacts_100k", bench_c5), ("PW", "pairwise_rmsd_matrix", bench_pairwise),
+                 ("ING", "ingest_from_reader", bench_ingest))
         for key, name, fn in table:
-            if key not in wanted:
+            if key not in wanted or (key == "ING" and not ctx.cpu):
                 continue
             t0 = time.perf_counter()
             try:
@@ -1115,7 +1190,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU (default: the C2 workload)")
     ap.add_argument("--atoms", type=int, default=N_O, help="O sites per frame (default: the C2 workload)")
-    ap.add_argument("--configs", default="C1,C2T,C3,C4,C5,PW", help="secondary configs to run")
+    ap.add_argument("--configs", default="C1,C2T,C3,C4,C5,PW,ING", help="secondary configs to run")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--quick", action="store_true", help="smaller secondary shapes (smoke runs)")

@@ -71,6 +71,13 @@ MDAGPU_API int mdagpu_device_count(int *count);
 MDAGPU_API int mdagpu_set_device(int device);
 /* number of kernel launches issued by this library in this process so far */
 MDAGPU_API unsigned long long mdagpu_launch_count(void);
+
+/* Copies between caller-owned host memory and device memory in stream order (csrc/hostcopy.cu):
+ * pageable host memory is staged through a pinned ring by a pool of host threads (about 40 GB/s
+ * against the driver's 10-20 GB/s), pinned memory goes straight to the DMA engine.
+ * host_to_device returns once `host` has been read; device_to_host once `host` holds the data. */
+MDAGPU_API int mdagpu_host_to_device(void *dev, const void *host, uint64_t bytes, mdagpu_stream_t stream);
+MDAGPU_API int mdagpu_device_to_host(void *host, const void *dev, uint64_t bytes, mdagpu_stream_t stream);
 /* Per-kernel device timing for benchmarks: when enabled, CUDA events bracket every
  * launch on its stream; mdagpu_profile_report() synchronises, writes
  * "name<TAB>launches<TAB>total_ms" lines into buf and clears the records. */

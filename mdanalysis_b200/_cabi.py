@@ -30,6 +30,8 @@ SIGNATURES = {
     "mdagpu_device_count": (_i, [C.POINTER(_i)]),
     "mdagpu_set_device": (_i, [_i]),
     "mdagpu_launch_count": (C.c_ulonglong, []),
+    "mdagpu_host_to_device": (_i, [_vp, _vp, _u64, _vp]),
+    "mdagpu_device_to_host": (_i, [_vp, _vp, _u64, _vp]),
     "mdagpu_profile_enable": (_i, [_i]),
     "mdagpu_profile_report": (_i, [C.c_char_p, _u64]),
     "mdagpu_distance_array": (_i, [_vp, _u64, _vp, _u64, _i, _vp, _vp, _u64, _i, _vp]),
@@ -164,3 +166,30 @@ def same_device(*tensors):
     devs = {t.device for t in tensors if t is not None and is_tensor(t)}
     if len(devs) > 1:
         raise ValueError(f"all tensor arguments must be on the same device, got {sorted(map(str, devs))}")
+
+
+def upload(array, device=None):
+    """NumPy array -> torch CUDA tensor of the same shape / dtype through the library's staged copy
+    (``mdagpu_host_to_device``): pageable arrays move at about PCIe rate instead of the driver's
+    pageable path that ``torch.as_tensor(a).cuda()`` takes."""
+    import numpy as np
+    import torch
+    a = np.ascontiguousarray(array)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device in (None, "cuda", True) else torch.device(device)
+    out = torch.empty(a.shape, dtype=torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype, device=dev)
+    if a.size:
+        check(load().mdagpu_host_to_device(tensor_ptr(out), ptr(a), a.nbytes, current_stream(out)))
+        torch.cuda.current_stream(dev).synchronize()      # `a` may be freed by the caller
+    return out
+
+
+def download(tensor, out=None):
+    """torch CUDA tensor -> NumPy array through ``mdagpu_device_to_host`` (staged for pageable ``out``)."""
+    import numpy as np
+    import torch
+    t = tensor.contiguous()
+    if out is None:
+        out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+    if t.numel():
+        check(load().mdagpu_device_to_host(ptr(out), tensor_ptr(t), out.nbytes, current_stream(t)))
+    return out

@@ -3,7 +3,7 @@
 """
 import numpy as np
 
-from .._cabi import DEVICE, check, current_stream, is_tensor, load, tensor_ptr
+from .._cabi import DEVICE, check, current_stream, download, is_tensor, load, tensor_ptr, upload
 from ..frames import as_block
 from ..lib import qcprot as qcp
 from .base import BlockAnalysis
@@ -134,13 +134,13 @@ class AverageStructure(BlockAnalysis):
             w = w / np.mean(w)
         import torch
         host_input = not blk.on_device
-        pos = torch.as_tensor(blk.positions).cuda() if host_input else blk.positions     # reduce on the device
+        pos = upload(blk.positions) if host_input else blk.positions     # reduce on the device
         vals, _, moved = qcp.qcp_trajectory(
             pos, self._ref_sel, select=self._sel_m, weights=w, align=True, convention=1,
             allclose_shortcut=(w is None), out=pos if (self._in_memory or host_input) else None)
         if self._in_memory:
             if host_input:
-                blk.positions[...] = moved.cpu().numpy()
+                download(moved, out=blk.positions)
             else:
                 blk.positions = moved
         # float64 mean over the frames of the fitted atoms: mdagpu_frame_mean (csrc/reduce.cu)

@@ -9,7 +9,7 @@ import functools
 import numpy as np
 
 from .._cabi import (BOX_NONE, BOX_ORTHO, BOX_TRICLINIC, DEVICE, HOST, check, current_stream, is_tensor,
-                     load, ptr, tensor_ptr)
+                     load, ptr, tensor_ptr, upload)
 from ..frames import FrameBlock, as_block
 from ..lib.distances import _box_args, distance_array
 from ..lib.util import check_box
@@ -196,7 +196,7 @@ class Contacts(BlockAnalysis):
         A = blk.select(self._idx[0]).positions
         B = blk.select(self._idx[1]).positions
         if not blk.on_device:
-            A, B = torch.as_tensor(A).to(dev), torch.as_tensor(B).to(dev)
+            A, B = upload(A, dev), upload(B, dev)
         dims = blk.dimensions if self.pbc else None
         kw = self.fraction_kwargs
         builtin = {"hard_cut": 0, "radius_cut": 1, "soft_cut": 2}.get(self._method_name)

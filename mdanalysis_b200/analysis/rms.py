@@ -12,7 +12,7 @@ is resolved through ``select_atoms``.
 """
 import numpy as np
 
-from .._cabi import DEVICE, check, current_stream, is_tensor, load, tensor_ptr
+from .._cabi import DEVICE, check, current_stream, is_tensor, load, tensor_ptr, upload
 from ..frames import FrameBlock, as_block
 from ..lib import qcprot as qcp
 from .base import BlockAnalysis
@@ -161,7 +161,7 @@ class RMSD(BlockAnalysis):
         # secondary groups: superpose whole frames (rms.py:697-721), then plain RMSDs of the groups,
         # reduced on the device in float64
         import torch
-        pos = blk.positions if blk.on_device else torch.as_tensor(blk.positions).cuda()
+        pos = blk.positions if blk.on_device else upload(blk.positions)
         vals, _, moved = qcp.qcp_trajectory(pos, self._ref_sel, select=self._sel_m,
                                             weights=w, align=True, convention=0)
         out[:, 2] = vals.detach().cpu().numpy()

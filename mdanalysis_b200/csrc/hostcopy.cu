@@ -223,3 +223,21 @@ cudaError_t device_to_host(void *host, const void *dev, size_t bytes, cudaStream
 }
 
 }  // namespace mdagpu
+
+using namespace mdagpu;
+
+// Public face of the two movers: torch tensors filled from / drained into NumPy arrays at the
+// staged rate (FrameBlock.to_device; torch's own .cuda() of a pageable array takes the driver's path).
+extern "C" int mdagpu_host_to_device(void *dev, const void *host, uint64_t bytes, mdagpu_stream_t stream)
+{
+    MDA_REQUIRE(bytes == 0 || (dev && host), "mdagpu_host_to_device: NULL argument");
+    MDA_CUDA(host_to_device(dev, host, bytes, (cudaStream_t)stream));
+    return MDAGPU_OK;
+}
+
+extern "C" int mdagpu_device_to_host(void *host, const void *dev, uint64_t bytes, mdagpu_stream_t stream)
+{
+    MDA_REQUIRE(bytes == 0 || (dev && host), "mdagpu_device_to_host: NULL argument");
+    MDA_CUDA(device_to_host(host, dev, bytes, (cudaStream_t)stream));
+    return MDAGPU_OK;
+}

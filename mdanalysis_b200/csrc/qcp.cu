@@ -105,13 +105,28 @@ qcp_ref_kernel(const float *__restrict__ ref, const double *__restrict__ w, uint
     }
 }
 
+// float -> double without the (quarter-rate) conversion unit: exact for normal numbers,
+// everything else takes the hardware conversion.
+__device__ __forceinline__ double f2d_alu(float x)
+{
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t e = b & 0x7f800000u;
+    if (e == 0u || e == 0x7f800000u) return (double)x;
+    const uint32_t hi = (b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u);
+    return __hiloint2double((int)hi, (int)(b << 29));
+}
+
 // accumulate one atom: y' = y - pivot (exact in double), xw = w (x - x_com)
 template <bool WEIGHTED>
 __device__ __forceinline__ void qcp_accumulate(double (&acc)[13], float fx, float fy, float fz,
                                                double px, double py, double pz, double xw0, double xw1,
                                                double xw2, double wi)
 {
+#if QCP_F2D_ALU
+    const double y0 = f2d_alu(fx) - px, y1 = f2d_alu(fy) - py, y2 = f2d_alu(fz) - pz;
+#else
     const double y0 = (double)fx - px, y1 = (double)fy - py, y2 = (double)fz - pz;
+#endif
     acc[0] = fma(y0, xw0, acc[0]); acc[1] = fma(y0, xw1, acc[1]); acc[2] = fma(y0, xw2, acc[2]);
     acc[3] = fma(y1, xw0, acc[3]); acc[4] = fma(y1, xw1, acc[4]); acc[5] = fma(y1, xw2, acc[5]);
     acc[6] = fma(y2, xw0, acc[6]); acc[7] = fma(y2, xw1, acc[7]); acc[8] = fma(y2, xw2, acc[8]);
@@ -294,28 +309,27 @@ qcp_traj_kernel(const float *traj, uint64_t natoms, const int32_t *__restrict__ 
 // No registers are spent on loads in flight: up to ~144 kB per SM are in flight.
 // With `aligned`, the same ring streams the 4 frames a second time (L2-resident:
 // 148 x 4 frames x 120 kB) and the consumers apply the rigid transform.
-constexpr int QS_CH = 1024;                 // atoms per chunk
+#ifndef QS_CH_
+#define QS_CH_ 1024
+#endif
+#ifndef QCP_F2D_ALU
+#define QCP_F2D_ALU 0
+#endif
+constexpr int QS_CH = QS_CH_;               // atoms per chunk
 constexpr int QS_FB = 4;                    // frames per batch = consumer groups
 constexpr int QS_GT = 128;                  // threads per group
 constexpr int QS_THREADS = QS_FB * QS_GT;
 constexpr int QS_REF_BYTES = QS_CH * 3 * 8;          // 6 planes x 256 double2
 constexpr int QS_W_BYTES = QS_CH * 8;                // 2 planes x 256 double2
 constexpr int QS_FRAME_BYTES = QS_CH * 12;
+// ring depth: as many stages as fit next to ~9 kB of static shared memory in the 227 kB of an SM
+constexpr int QS_SMEM_BUDGET = 216 * 1024;
+constexpr int QS_STAGES_U = QS_SMEM_BUDGET / (QS_REF_BYTES + QS_FB * QS_FRAME_BYTES);
+constexpr int QS_STAGES_W = QS_SMEM_BUDGET / (QS_REF_BYTES + QS_W_BYTES + QS_FB * QS_FRAME_BYTES);
 
 __device__ __forceinline__ void group_sync(int group)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(QS_GT) : "memory");
-}
-
-// float -> double without the (quarter-rate) conversion unit: exact for normal numbers,
-// everything else takes the hardware conversion.
-__device__ __forceinline__ double f2d_alu(float x)
-{
-    const uint32_t b = __float_as_uint(x);
-    const uint32_t e = b & 0x7f800000u;
-    if (e == 0u || e == 0x7f800000u) return (double)x;
-    const uint32_t hi = (b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u);
-    return __hiloint2double((int)hi, (int)(b << 29));
 }
 
 // chunked plane layout of the centred reference: for chunk c, plane p (0..5), quad q (0..255)
@@ -750,14 +764,15 @@ extern "C" int mdagpu_qcp_trajectory(const float *traj, uint64_t nframes, uint64
         const uint64_t nbatch = (nframes + QS_FB - 1) / QS_FB;
         const unsigned grid = (unsigned)(nbatch < (uint64_t)num_sms() ? nbatch : (uint64_t)num_sms());
         // ring depth: as many stages as fit in the 227 kB of one SM (3 x 72 kB, or 2 x 80 kB with weights)
+        constexpr int SW = QS_STAGES_W, SU = QS_STAGES_U;
         if (weights) {
-            const size_t smem = 2 * (size_t)(QS_REF_BYTES + QS_W_BYTES + QS_FB * QS_FRAME_BYTES);
-            MDA_CUDA(cudaFuncSetAttribute(qcp_stream_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<true, 2>), grid, QS_THREADS + 32, smem, st, qp);
+            const size_t smem = SW * (size_t)(QS_REF_BYTES + QS_W_BYTES + QS_FB * QS_FRAME_BYTES);
+            MDA_CUDA(cudaFuncSetAttribute(qcp_stream_kernel<true, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<true, SW>), grid, QS_THREADS + 32, smem, st, qp);
         } else {
-            const size_t smem = 3 * (size_t)(QS_REF_BYTES + QS_FB * QS_FRAME_BYTES);
-            MDA_CUDA(cudaFuncSetAttribute(qcp_stream_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<false, 3>), grid, QS_THREADS + 32, smem, st, qp);
+            const size_t smem = SU * (size_t)(QS_REF_BYTES + QS_FB * QS_FRAME_BYTES);
+            MDA_CUDA(cudaFuncSetAttribute(qcp_stream_kernel<false, SU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MDA_LAUNCH_AS("qcp_stream_kernel", (qcp_stream_kernel<false, SU>), grid, QS_THREADS + 32, smem, st, qp);
         }
         MDA_CHECK_LAUNCH();
         MDA_CUDA(rm.finish());

@@ -91,9 +91,8 @@ class FrameBlock:
     def to_device(self, device="cuda"):
         if self.on_device:
             return self
-        import torch
-        return FrameBlock(torch.as_tensor(self.positions).to(device), self.dimensions, self.frames,
-                          self.times, self.masses)
+        from ._cabi import upload
+        return FrameBlock(upload(self.positions, device), self.dimensions, self.frames, self.times, self.masses)
 
     @classmethod
     def from_atomgroup(cls, atomgroup, start=None, stop=None, step=None, frames=None):
@@ -148,7 +147,9 @@ class FrameBlock:
         if kind == "MemoryReader" and plain:
             arr = traj.get_array()
             order = traj.stored_order
-            pos = np.transpose(arr, (order.find("f"), order.find("a"), order.find("c")))[fidx]
+            view = np.transpose(arr, (order.find("f"), order.find("a"), order.find("c")))
+            # a regular frame range is a VIEW of the reader's array (no copy of the trajectory)
+            pos = view[regular] if regular is not None else view[fidx]
             if not whole:
                 pos = pos[:, aidx]
             dims = np.asarray(traj.dimensions_array, dtype=np.float32)[fidx]
