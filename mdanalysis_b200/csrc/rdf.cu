@@ -419,18 +419,49 @@ bbox_kernel(const float *__restrict__ xyz, uint64_t total, float *__restrict__ l
     }
 }
 
-// Two-buffer upload ring for host-resident frames: piece k is copied on a private stream
-// into buffer k & 1 (after the kernels that read the buffer two pieces ago have finished)
+// The three "this piece cannot go through the planner / walker pair" flags of a piece in one word
+// triple that the host reads one piece later (no host synchronisation inside a piece).
+__global__ void rdf_flags_kernel(const unsigned *over, const unsigned *bad0, const unsigned *bad1, unsigned *out3)
+{
+    out3[0] = over ? *over : 0u;
+    out3[1] = bad0 ? *bad0 : 0u;
+    out3[2] = bad1 ? *bad1 : 0u;
+}
+
+// pinned landing slots for those flags (per thread, reused by every call)
+struct FlagSlots {
+    static constexpr int N = 64;
+    unsigned *host = nullptr;
+    cudaEvent_t ev[N] = { nullptr };
+    cudaError_t init()
+    {
+        if (host) return cudaSuccess;
+        cudaError_t e = cudaHostAlloc((void **)&host, N * 4 * sizeof(unsigned), cudaHostAllocDefault);
+        for (int k = 0; k < N && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+        return e;
+    }
+};
+static FlagSlots &flag_slots()
+{
+    static thread_local FlagSlots fs[8];          // recursion depth of rdf_accumulate_impl is 2; per device below
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return fs[dev & 7];
+}
+
+// Upload ring for host-resident frames: piece k is copied on a private stream
+// into buffer k % NB (after the kernels that read the buffer NB pieces ago have finished)
 // and the compute stream waits for the copy before it touches the buffer.
 struct HostPipe {
     const float *A = nullptr, *B = nullptr;
     uint64_t na = 0, nb = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
-    cudaEvent_t ready[2] = { nullptr, nullptr }, freed[2] = { nullptr, nullptr };
-    DevBuf abuf[2], bbuf[2];
+    static constexpr int NB = 3;                      // buffers: uploads run up to two pieces ahead of the kernels
+    cudaEvent_t ready[NB] = { nullptr }, freed[NB] = { nullptr };
+    DevBuf abuf[NB], bbuf[NB];
     ~HostPipe()
     {
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < NB; ++k) {
             if (ready[k]) cudaEventDestroy(ready[k]);
             if (freed[k]) cudaEventDestroy(freed[k]);
         }
@@ -443,7 +474,7 @@ struct HostPipe {
     {
         A = a; B = b; na = na_; nb = nb_; compute = st;
         cudaError_t e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking);
-        for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        for (int k = 0; k < NB && e == cudaSuccess; ++k) {
             e = cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming);
             if (e == cudaSuccess) e = abuf[k].alloc(piece * na * 3 * sizeof(float), st);
@@ -453,24 +484,11 @@ struct HostPipe {
         }
         return e;
     }
-    // Pinned frames: the DMA is queued at once and runs under the kernels of the piece before.
-    // Pageable frames are staged by host threads (hostcopy.cu), which blocks this thread: that
-    // upload is deferred until the kernels of the current piece have been launched (release()).
-    bool deferred = false;
-    uint64_t d_piece = 0, d_f0 = 0, d_fc = 0;
     cudaError_t upload(uint64_t piece_no, uint64_t f0, uint64_t fc)
     {
-        if (piece_no > 0 && !(host_is_pinned(A + f0 * na * 3) && (!B || host_is_pinned(B + f0 * nb * 3)))) {
-            deferred = true;
-            d_piece = piece_no; d_f0 = f0; d_fc = fc;
-            return cudaSuccess;
-        }
-        return upload_now(piece_no, f0, fc);
-    }
-    cudaError_t upload_now(uint64_t piece_no, uint64_t f0, uint64_t fc)
-    {
-        const int k = (int)(piece_no & 1);
-        cudaError_t e = cudaStreamWaitEvent(copy, freed[k], 0);
+        const int k = (int)(piece_no % NB);
+        cudaError_t e = done[k] ? cudaSuccess : cudaStreamWaitEvent(copy, freed[k], 0);
+        done[k] = false;
         if (e == cudaSuccess)
             e = host_to_device(abuf[k].p, A + f0 * na * 3, fc * na * 3 * sizeof(float), copy);
         if (e == cudaSuccess && B)
@@ -480,20 +498,16 @@ struct HostPipe {
     }
     cudaError_t acquire(uint64_t piece_no, const float **a, const float **b)
     {
-        const int k = (int)(piece_no & 1);
+        const int k = (int)(piece_no % NB);
         *a = abuf[k].as<float>();
         *b = B ? bbuf[k].as<float>() : nullptr;
         return cudaStreamWaitEvent(compute, ready[k], 0);
     }
-    cudaError_t release(uint64_t piece_no)
-    {
-        cudaError_t e = cudaEventRecord(freed[(int)(piece_no & 1)], compute);
-        if (e == cudaSuccess && deferred) {
-            deferred = false;
-            e = upload_now(d_piece, d_f0, d_fc);
-        }
-        return e;
-    }
+    cudaError_t release(uint64_t piece_no) { return cudaEventRecord(freed[(int)(piece_no % NB)], compute); }
+    // the host has SEEN the piece finish (it synchronised on something behind its kernels): no event --
+    // one recorded now would sit behind the kernels of the pieces queued since
+    bool done[NB] = { false };
+    void release_completed(uint64_t piece_no) { done[(int)(piece_no % NB)] = true; }
 };
 
 }  // namespace mdagpu
@@ -683,24 +697,30 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
         if (chunk > by_cells) chunk = by_cells;
     }
 
-    // Host input is streamed: frames go up in pieces on a second stream into a two-buffer
-    // ring while the previous piece is being binned (the reference-facing call hands over
+    // Host input is streamed: frames go up in pieces on a second stream into a ring of
+    // buffers while the pieces before are being binned (the reference-facing call hands over
     // HOST arrays; 400 MB per 1000 frames of C2 would otherwise sit in front of the kernels).
+    // A piece is a quarter of the call (measured: 1/3 ... 1/16 make no difference, profiles/r02_notes.md):
+    // staging a piece (pageable frames: ~36 GB/s through the pinned ring, on this thread) takes half the
+    // time its kernels do and uploads run up to two pieces ahead; the first pieces are smaller --
+    // their upload is the one nothing hides.
     HostPipe pipe;
     if (space == MDAGPU_HOST) {
-        uint64_t piece = (nframes + 3) / 4;
+        static const int div_env = getenv("MDAGPU_RDF_PIECE_DIV") ? atoi(getenv("MDAGPU_RDF_PIECE_DIV")) : 0;
+        const uint64_t div = div_env > 0 ? (uint64_t)div_env : 4;
+        uint64_t piece = (nframes + div - 1) / div;
         if (piece < 16) piece = 16;
         if (chunk > piece) chunk = piece;
         MDA_CUDA(pipe.init(A, same ? nullptr : B, na, nb, chunk, st));
     }
 
-    // piece schedule: device input in equal chunks; host input starts small (the first upload is
-    // the only one nothing hides) and doubles up to the ring's buffer size
+    // piece schedule: device input in equal chunks; host input starts at an eighth of a piece and doubles
     std::vector<uint64_t> piece_start;
     {
         uint64_t size = chunk;
         if (space == MDAGPU_HOST) {
-            size = chunk / 16;
+            static const int ramp_env = getenv("MDAGPU_RDF_RAMP_DIV") ? atoi(getenv("MDAGPU_RDF_RAMP_DIV")) : 0;
+            size = chunk / (ramp_env > 0 ? (uint64_t)ramp_env : 8);
             if (size < 16) size = 16;
             if (size > chunk) size = chunk;
         }
@@ -713,16 +733,64 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     }
 
     DevBuf fg_dev;
+    // Upload ring bookkeeping: piece p may go up once piece p - NB has been released.
+    const uint64_t n_pieces = piece_start.size() - 1;
+    uint64_t next_upload = 0, n_released = 0;
+    auto pump = [&]() -> cudaError_t {
+        while (space == MDAGPU_HOST && next_upload < n_pieces && next_upload < n_released + HostPipe::NB) {
+            cudaError_t e = pipe.upload(next_upload, piece_start[next_upload], piece_start[next_upload + 1] - piece_start[next_upload]);
+            if (e != cudaSuccess) return e;
+            ++next_upload;
+        }
+        return cudaSuccess;
+    };
+    auto release_piece = [&](uint64_t p, bool seen_complete = false) -> cudaError_t {
+        if (space != MDAGPU_HOST) return cudaSuccess;
+        cudaError_t e = cudaSuccess;
+        if (seen_complete) pipe.release_completed(p);
+        else e = pipe.release(p);
+        ++n_released;
+        return e == cudaSuccess ? pump() : e;
+    };
+    // Pieces of the planner / walker path whose flags the host has not looked at yet.  The walker
+    // skips a flagged piece on the device; the host reads the flags ONE PIECE LATER -- by then the
+    // next piece is queued behind it, so the device never waits for the host -- and sends a
+    // flagged piece through the other kernels.  Only then is the piece's upload buffer released.
+    struct Pending { uint64_t piece, f0, fc; const float *a, *b; int slot; };
+    std::vector<Pending> pending;
+    int slots_used = 0;
+    auto settle = [&](size_t keep) -> int {
+        while (pending.size() > keep) {
+            const Pending pd = pending.front();
+            pending.erase(pending.begin());
+            FlagSlots &fs = flag_slots();
+            MDA_CUDA(cudaEventSynchronize(fs.ev[pd.slot]));
+            const unsigned *fl = fs.host + 4 * pd.slot;
+            if (fl[0] | fl[1] | fl[2]) {
+                const int how = (fl[1] | fl[2]) ? 1 : 2;           // folded atoms: reference grid; planner declined: no planner
+                if (getenv("MDAGPU_DEBUG"))
+                    fprintf(stderr, "mdagpu: rdf piece of %llu frames redone without the planner (flags %u %u %u)\n",
+                            (unsigned long long)pd.fc, fl[0], fl[1], fl[2]);
+                int rc2 = rdf_accumulate_impl(pd.a, na, same ? nullptr : pd.b, nb, pd.fc, boxes_per_frame ? box6 + 6 * pd.f0 : box6,
+                                              boxes_per_frame ? h9 + 9 * pd.f0 : h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
+                                              use_grid, thresholds, nbins, r_lo, r_hi, (same && !report_self) ? 1 : excl_a,
+                                              (same && !report_self) ? 1 : excl_b, ids_a_host, ids_b_host,
+                                              cnt.as<unsigned long long>(), per_site, MDAGPU_DEVICE, stream, how);
+                if (rc2) return rc2;
+            }
+            // (a redone piece queued new kernels that read the buffer: then the event is needed)
+            MDA_CUDA(release_piece(pd.piece, !(fl[0] | fl[1] | fl[2])));
+        }
+        return MDAGPU_OK;
+    };
+    if (space == MDAGPU_HOST) {                           // only piece 0 goes up before the first kernels are queued
+        MDA_CUDA(pipe.upload(0, piece_start[0], piece_start[1] - piece_start[0]));
+        next_upload = 1;
+    }
     for (uint64_t piece_no = 0; piece_no + 1 < piece_start.size(); ++piece_no) {
         const uint64_t f0 = piece_start[piece_no], fc = piece_start[piece_no + 1] - f0;
         const float *a_dev = A + f0 * na * 3, *b_dev = same ? nullptr : B + f0 * nb * 3;
-        if (space == MDAGPU_HOST) {
-            if (piece_no == 0) MDA_CUDA(pipe.upload(0, f0, fc));
-            if (piece_no + 2 < piece_start.size())
-                MDA_CUDA(pipe.upload(piece_no + 1, piece_start[piece_no + 1],
-                                     piece_start[piece_no + 2] - piece_start[piece_no + 1]));
-            MDA_CUDA(pipe.acquire(piece_no, &a_dev, &b_dev));
-        }
+        if (space == MDAGPU_HOST) MDA_CUDA(pipe.acquire(piece_no, &a_dev, &b_dev));
         uint64_t total_cells;
         if (boxes_per_frame) {
             // re-base this chunk's cells at zero
@@ -756,7 +824,9 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
         tv.row = W > 0;
         tv.quad = quad;
         tv.chunks = 1;
-        if (tv.row) {
+        const bool lagged = fineWX && tv.row && flag_slots().init() == cudaSuccess;
+        if (!lagged) { const int rs = settle(0); if (rs) return rs; }       // these paths synchronise themselves
+        if (tv.row && !lagged) {
             // an atom that the float64 cell arithmetic folded into a cell it does not lie
             // in (a coordinate the reference's wrap left ON the upper face of the cell, e.g.
             // -1e-7 + L == L in float32) breaks the per-cell image prediction: the per-pair
@@ -775,12 +845,12 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
                                          (same && !report_self) ? 1 : excl_b, ids_a_host, ids_b_host,
                                              cnt.as<unsigned long long>(), per_site, MDAGPU_DEVICE, stream, 1);
                     if (rc) return rc;
-                    if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
+                    MDA_CUDA(release_piece(piece_no));
                     continue;
                 }
             }
         }
-        if (fineWX && tv.row) {
+        if (lagged) {
             // rowfine.cuh: a CTA owns R fine home cells of a (y, z) row (the whole row when its queries fit
             // 224 threads and the staged rows fit the tile); a planner kernel writes row descriptors and
             // sorted window records, the walker stages and bins.  Densities the two cannot take (tile,
@@ -824,26 +894,14 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             if (same)
                 MDA_LAUNCH_AS("rdf_window_planner", (fine_plan_kernel<true, 224>), grid, 224, plan_smem, st, cl.atoms(), cl.start(),
                               cl.start(), fgd, boxes_per_frame, fgs[boxes_per_frame ? f0 : 0], fp, RF_CAP, list_cap,
-                              units.as<FineUnit<13>>(), lists.as<uint32_t>(), oflag.as<unsigned>());
+                              units.as<FineUnit<13>>(), lists.as<uint32_t>(), oflag.as<unsigned>(), cl.inconsistent(),
+                              (const unsigned *)nullptr);
             else
                 MDA_LAUNCH_AS("rdf_window_planner", (fine_plan_kernel<false, 224>), grid, 224, plan_smem, st, ql.atoms(), ql.start(),
                               cl.start(), fgd, boxes_per_frame, fgs[boxes_per_frame ? f0 : 0], fp, RF_CAP, list_cap,
-                              units.as<FineUnit<25>>(), lists.as<uint32_t>(), oflag.as<unsigned>());
+                              units.as<FineUnit<25>>(), lists.as<uint32_t>(), oflag.as<unsigned>(), cl.inconsistent(),
+                              ql.inconsistent());
             MDA_CHECK_LAUNCH();
-            unsigned over = 0u;
-            MDA_CUDA(cudaMemcpyAsync(&over, oflag.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            MDA_CUDA(cudaStreamSynchronize(st));
-            if (over) {
-                if (getenv("MDAGPU_DEBUG")) fprintf(stderr, "mdagpu: rdf planner declined (flags %u), piece of %llu frames\n", over, (unsigned long long)fc);
-                rc = rdf_accumulate_impl(a_dev, na, same ? nullptr : b_dev, nb, fc, boxes_per_frame ? box6 + 6 * f0 : box6,
-                                         boxes_per_frame ? h9 + 9 * f0 : h9, boxes_per_frame, mic, wrap, cutoff, d2_max,
-                                         use_grid, thresholds, nbins, r_lo, r_hi, (same && !report_self) ? 1 : excl_a,
-                                         (same && !report_self) ? 1 : excl_b, ids_a_host, ids_b_host,
-                                         cnt.as<unsigned long long>(), per_site, MDAGPU_DEVICE, stream, 2);
-                if (rc) return rc;
-                if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
-                continue;
-            }
             // lane columns of the histogram: 16 keep four CTAs on an SM (55 kB each)
             int ls = 4;
             while (ls > 0 && ((size_t)(nbins + 2) << ls) * sizeof(uint32_t) > 10 * 1024) --ls;
@@ -868,21 +926,35 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
                     if (same)
                         MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>), g1, 224, total, st,
                                       cl.atoms(), cl.atoms(), units.as<FineUnit<13>>() + ff * units_x,
-                                      lists.as<uint32_t>() + ff * units_x * list_cap, list_cap, bxf, spc, sink);
+                                      lists.as<uint32_t>() + ff * units_x * list_cap, list_cap, bxf, spc, sink, oflag.as<unsigned>(), cl.inconsistent(), same ? (const unsigned *)nullptr : ql.inconsistent());
                     else
                         MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>), g1, 224, total, st,
                                       ql.atoms(), cl.atoms(), units.as<FineUnit<25>>() + ff * units_x,
-                                      lists.as<uint32_t>() + ff * units_x * list_cap, list_cap, bxf, spc, sink);
+                                      lists.as<uint32_t>() + ff * units_x * list_cap, list_cap, bxf, spc, sink, oflag.as<unsigned>(), cl.inconsistent(), same ? (const unsigned *)nullptr : ql.inconsistent());
                 }
             } else if (same) {
                 MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>), grid, 224, total, st,
-                              cl.atoms(), cl.atoms(), units.as<FineUnit<13>>(), lists.as<uint32_t>(), list_cap, bx, spc, sink);
+                              cl.atoms(), cl.atoms(), units.as<FineUnit<13>>(), lists.as<uint32_t>(), list_cap, bx, spc, sink, oflag.as<unsigned>(), cl.inconsistent(), (const unsigned *)nullptr);
             } else {
                 MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>), grid, 224, total, st,
-                              ql.atoms(), cl.atoms(), units.as<FineUnit<25>>(), lists.as<uint32_t>(), list_cap, bx, spc, sink);
+                              ql.atoms(), cl.atoms(), units.as<FineUnit<25>>(), lists.as<uint32_t>(), list_cap, bx, spc, sink, oflag.as<unsigned>(), cl.inconsistent(), ql.inconsistent());
             }
             MDA_CHECK_LAUNCH();
-            if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
+            {
+                // flags of this piece -> pinned slot; looked at after the NEXT piece has been queued
+                FlagSlots &fs = flag_slots();
+                const int slot = slots_used++ % FlagSlots::N;
+                DevBuf f3;
+                MDA_CUDA(f3.alloc(3 * sizeof(unsigned), st));
+                MDA_LAUNCH(rdf_flags_kernel, 1, 1, 0, st, oflag.as<unsigned>(), cl.inconsistent(),
+                           same ? (const unsigned *)nullptr : ql.inconsistent(), f3.as<unsigned>());
+                MDA_CUDA(cudaMemcpyAsync(fs.host + 4 * slot, f3.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                MDA_CUDA(cudaEventRecord(fs.ev[slot], st));
+                pending.push_back({ piece_no, f0, fc, a_dev, b_dev, slot });
+                const int rs = settle(1);
+                if (rs) return rs;
+                MDA_CUDA(pump());                        // (the first iterations: nothing released yet, buffers still free)
+            }
             continue;
         }
         int threads;
@@ -961,8 +1033,9 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
 #undef RUN_HIST
 #undef COMMA
         if (rc) return rc;
-        if (space == MDAGPU_HOST) MDA_CUDA(pipe.release(piece_no));
+        MDA_CUDA(release_piece(piece_no));
     }
+    { const int rs = settle(0); if (rs) return rs; }
     MDA_CUDA(cnt.finish());
     if (space == MDAGPU_HOST) MDA_CUDA(cudaStreamSynchronize(st));
     return MDAGPU_OK;

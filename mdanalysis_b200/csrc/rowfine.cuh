@@ -222,8 +222,12 @@ __global__ void __launch_bounds__(T, 6)
 fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
                  const uint32_t *__restrict__ c_start, const FrameGeom *__restrict__ fgs, int per_frame,
                  const __grid_constant__ FrameGeom fg_const, FineParams fp, int cap, int list_cap,
-                 FineUnit<SELF ? 13 : 25> *__restrict__ units, uint32_t *__restrict__ lists, unsigned *__restrict__ flag)
+                 FineUnit<SELF ? 13 : 25> *__restrict__ units, uint32_t *__restrict__ lists, unsigned *__restrict__ flag,
+                 const unsigned *__restrict__ bad0, const unsigned *__restrict__ bad1)
 {
+    // a cell list with folded atoms (engine.cuh: inconsistent) is not planned: the host sends the
+    // piece to the per-pair kernels when it reads the flags, one piece later
+    if ((bad0 && *bad0) || (bad1 && *bad1)) return;
     constexpr int NW = T / 32;
     constexpr int NR = SELF ? 13 : 25;                             // rows of the stencil (W = 2)
     constexpr int NB = 2 * RF_WMAX;                                // (home?, length) buckets
@@ -506,8 +510,12 @@ template <bool SELF, class Sink, int CAP, int MIN_CTAS>
 __global__ void __launch_bounds__(Sink::THREADS, MIN_CTAS)
 fine_walk_kernel(const float4 *__restrict__ q_atoms, const float4 *__restrict__ c_atoms,
                  const FineUnit<SELF ? 13 : 25> *__restrict__ units, const uint32_t *__restrict__ lists, int list_cap,
-                 const __grid_constant__ BoxParams box, SearchParams sp, Sink sink)
+                 const __grid_constant__ BoxParams box, SearchParams sp, Sink sink,
+                 const unsigned *__restrict__ skip0, const unsigned *__restrict__ skip1, const unsigned *__restrict__ skip2)
 {
+    // the planner declined (skip0) or a cell list has folded atoms (skip1, skip2): nothing of this
+    // piece is binned here -- the host reads the same flags and runs the piece through the other kernels
+    if ((skip0 && *skip0) || (skip1 && *skip1) || (skip2 && *skip2)) return;
     constexpr int T = Sink::THREADS, NW = T / 32;
     constexpr int NR = SELF ? 13 : 25;
     // dynamic shared memory: [histogram] [x, y, z planes of the staged rows]
