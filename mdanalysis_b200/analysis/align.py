@@ -7,7 +7,7 @@ from .._cabi import DEVICE, check, current_stream, download, is_tensor, load, te
 from ..frames import as_block
 from ..lib import qcprot as qcp
 from .base import BlockAnalysis
-from .rms import _resolve_selection, get_weights
+from .rms import _resolve_selection, _whole, get_weights
 
 
 def rotation_matrix(a, b, weights=None):
@@ -48,8 +48,9 @@ class AlignTraj(BlockAnalysis):
         blk = as_block(mobile)
         super().__init__(blk, **kwargs)
         self._ref = as_block(reference)
-        self._sel_m = _resolve_selection(mobile, select["mobile"] if isinstance(select, dict) else select)
-        self._sel_r = _resolve_selection(reference, select["reference"] if isinstance(select, dict) else select)
+        self._sel_m = _whole(_resolve_selection(mobile, select["mobile"] if isinstance(select, dict) else select), blk.n_atoms)
+        self._sel_r = _whole(_resolve_selection(reference, select["reference"] if isinstance(select, dict) else select),
+                             self._ref.n_atoms)
         self._weights = weights
         self._in_memory = in_memory
         self.ref_frame = ref_frame

@@ -51,6 +51,14 @@ def _resolve_selection(group, select):
     return np.asarray(select, dtype=np.int64)
 
 
+def _whole(sel, n_atoms):
+    """``None`` when the index list is every atom in order: the kernels then take the contiguous
+    (TMA-streamed) path instead of a gather through an index list that changes nothing."""
+    if sel is not None and len(sel) == n_atoms and np.array_equal(sel, np.arange(n_atoms)):
+        return None
+    return sel
+
+
 def get_weights(block, weights):
     """util.get_weights: None | 'mass' | array (lib/util.py:1329-1397)."""
     if weights is None:
@@ -95,6 +103,7 @@ class RMSD(BlockAnalysis):
         else:
             sel_m = _resolve_selection(atomgroup, select)
             sel_r = _resolve_selection(reference if reference is not None else atomgroup, select)
+        sel_m, sel_r = _whole(sel_m, mobile.n_atoms), _whole(sel_r, refblock.n_atoms)
         self._sel_m, self._sel_r = sel_m, sel_r
         self._refblock = refblock
         self.ref_frame = ref_frame
