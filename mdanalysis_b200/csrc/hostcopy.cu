@@ -99,6 +99,9 @@ int copy_threads()
     cpu_set_t set;
     int avail = 1;
     if (sched_getaffinity(0, sizeof set, &set) == 0) avail = CPU_COUNT(&set);
+    // one process per GPU (torchrun): the ranks of a node share its cores
+    const char *lws = getenv("LOCAL_WORLD_SIZE");
+    if (lws && atoi(lws) > 1) avail = avail / atoi(lws) > 1 ? avail / atoi(lws) : 1;
     // measured on the B200 box (16 cores, profiles/microbench/hostcopy_bench.txt): one thread moves
     // 9 GB/s, 8 threads 35-40 GB/s, 12 threads 41 GB/s of the 52 GB/s a pinned transfer reaches
     int n = avail - avail / 4;
