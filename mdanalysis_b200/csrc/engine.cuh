@@ -33,6 +33,8 @@ void grid_geometry_ortho_free(double cutoff, const float *L3, const double *orig
                               GridGeom *g);
 // a single cell holding everything (all-pairs / brute force)
 void grid_geometry_single(GridGeom *g);
+// bounding box of `total` points into lohi[6] = { min x, y, z, max x, y, z } (initialise with +-FLT_MAX; rdf.cu)
+__global__ void bbox_kernel(const float *__restrict__ xyz, uint64_t total, float *__restrict__ lohi);
 
 // Per frame-set description living in device memory (one entry per frame, or a
 // single entry shared by all frames).

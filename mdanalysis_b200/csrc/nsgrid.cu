@@ -572,27 +572,74 @@ extern "C" int mdagpu_capped_bruteforce(const float *ref, uint64_t n, const floa
     grid_geometry_single(&fg.grid);
     fg.box = make_box_params(box_mode, box);
     fg.cell_base = 0;
-    DevBuf fg_dev;
-    cudaError_t e = fg_dev.alloc(sizeof(FrameGeom), st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(fg_dev.p, &fg, sizeof(FrameGeom), cudaMemcpyHostToDevice, st);
     StagedIn r, c;
-    if (e == cudaSuccess) e = r.init(ref, n * 3 * sizeof(float), space, st);
+    cudaError_t e = r.init(ref, n * 3 * sizeof(float), space, st);
     if (e == cudaSuccess && !self) e = c.init(conf, m * 3 * sizeof(float), space, st);
-    if (e != cudaSuccess) { delete res; MDA_CUDA(e); }
     // the triclinic distance kernels work on wrapped copies (calc_distances.h:429-430);
     // every atom carries its original index, so the slot order does not matter.
-    const int wrap = box_mode == BOX_TRICLINIC;
+    int wrap = box_mode == BOX_TRICLINIC;
+    // Large inputs (the reference picks 'pkdtree' for them: thousands of atoms, cutoff a few per cent
+    // of the box): all-pairs would be O(n m).  Same float64 arithmetic, but the atoms are binned on a
+    // grid of cells >= max_cutoff and only the 27-cell stencil is visited -- orthorhombic boxes
+    // (binned by the wrapped position, evaluated on the coordinates as given) and no box (grid over
+    // the bounding box of both groups).  Triclinic cells keep the single cell.
+    int stencil = 0;
+    const uint64_t biggest = self ? n : (n > m ? n : m);
+    if (e == cudaSuccess && box_mode != BOX_TRICLINIC && biggest >= 8192 && max_cutoff > 0.0 && !getenv("MDAGPU_NO_BRUTE_GRID")) {
+        GridGeom g;
+        bool ok = true;
+        if (box_mode == BOX_ORTHO) {
+            grid_geometry_ortho_free(max_cutoff, box, nullptr, 1, &g);
+            wrap = 2;
+        } else {
+            DevBuf lohi;
+            e = lohi.alloc(6 * sizeof(float), st);
+            const float init[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
+            float h[6];
+            if (e == cudaSuccess) e = cudaMemcpyAsync(lohi.p, init, sizeof init, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) {
+                unsigned blocks = cdiv(n, 256);
+                if (blocks > (unsigned)num_sms() * 8) blocks = (unsigned)num_sms() * 8;
+                MDA_LAUNCH(bbox_kernel, blocks, 256, 0, st, r.as<float>(), n, lohi.as<float>());
+                if (!self) {
+                    blocks = cdiv(m, 256);
+                    if (blocks > (unsigned)num_sms() * 8) blocks = (unsigned)num_sms() * 8;
+                    MDA_LAUNCH(bbox_kernel, blocks, 256, 0, st, c.as<float>(), m, lohi.as<float>());
+                }
+                e = cudaMemcpyAsync(h, lohi.p, sizeof h, cudaMemcpyDeviceToHost, st);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e == cudaSuccess) {
+                float L[3];
+                double origin[3];
+                for (int k = 0; k < 3; ++k) {
+                    ok = ok && isfinite(h[k]) && isfinite(h[3 + k]);
+                    const double pad = 1e-3 + 1e-5 * fmax(fabs((double)h[k]), fabs((double)h[3 + k]));
+                    origin[k] = (double)h[k] - pad;
+                    L[k] = (float)((double)h[3 + k] - (double)h[k] + 2.0 * pad + max_cutoff * 1e-3);
+                }
+                if (ok) grid_geometry_ortho_free(max_cutoff, L, origin, 0, &g);
+            }
+        }
+        if (e == cudaSuccess && ok && g.ncell_total >= 27) { fg.grid = g; stencil = 1; }
+        else if (box_mode == BOX_ORTHO) wrap = 0;
+    }
+    DevBuf fg_dev;
+    if (e == cudaSuccess) e = fg_dev.alloc(sizeof(FrameGeom), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fg_dev.p, &fg, sizeof(FrameGeom), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { delete res; MDA_CUDA(e); }
     CellList rl, cl;
-    int rc = build_cell_list(r.as<float>(), n, 1, fg_dev.as<FrameGeom>(), 0, 1, wrap, st, &rl);
+    const uint64_t ncell = (uint64_t)fg.grid.ncell_total;
+    int rc = build_cell_list(r.as<float>(), n, 1, fg_dev.as<FrameGeom>(), 0, ncell, wrap, st, &rl);
     if (rc == MDAGPU_OK && !self)
-        rc = build_cell_list(c.as<float>(), m, 1, fg_dev.as<FrameGeom>(), 0, 1, wrap, st, &cl);
+        rc = build_cell_list(c.as<float>(), m, 1, fg_dev.as<FrameGeom>(), 0, ncell, wrap, st, &cl);
     if (rc == MDAGPU_OK) {
         SearchParams sp;
         sp.d2_max = d2_threshold_le(max_cutoff);
         sp.d2_min = min_cutoff >= 0.0 ? d2_threshold_le(min_cutoff) : -1.0;
         sp.d2_filter = filter_threshold(sp.d2_max, box_mode == BOX_TRICLINIC ? tric_abs_err(fg.box.h) : 0.0);
         sp.use_filter = box_mode != BOX_ORTHO;   // no safe FP32 bound for unwrapped ortho input
-        sp.stencil = 0;
+        sp.stencil = stencil;
         sp.include_self = 0;
         const int mic = box_mode == BOX_ORTHO ? MIC_ORTHO_ROUND : (box_mode == BOX_TRICLINIC ? MIC_TRICLINIC : MIC_NONE);
         const uint64_t guess = (self ? n * 32 : n * 64) + 4096;

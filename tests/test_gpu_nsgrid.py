@@ -118,6 +118,32 @@ def test_capped_distance(oracle, bname, method, mn):
     assert isinstance(p, np.ndarray) and p.shape[1] == 2
 
 
+@pytest.mark.parametrize("bname", ["none", "ortho"])
+def test_bruteforce_on_a_grid_for_large_inputs(oracle, bname, monkeypatch):
+    """method='bruteforce' / 'pkdtree' with >= 8192 atoms: same float64 arithmetic and pair orientation,
+    but binned on a grid of cells >= max_cutoff (csrc/nsgrid.cu mdagpu_capped_bruteforce) instead of
+    all pairs.  Input NOT wrapped into the box (atoms up to three boxes away), against the oracle's
+    all-pairs loop and against the library's own all-pairs path."""
+    from mdanalysis_b200.lib import distances as gd
+    rng = np.random.default_rng(77)
+    box = None if bname == "none" else np.array([60, 55, 70, 90, 90, 90], dtype=np.float32)
+    a = (rng.random((9000, 3)) * 60).astype(np.float32)
+    b = (rng.random((8500, 3)) * 60).astype(np.float32)
+    if box is not None:
+        a += (rng.integers(-3, 4, (9000, 3)) * box[:3]).astype(np.float32)
+        b[::7] -= box[:3] * 2
+    for mn in (None, 1.0):
+        got = gd.capped_distance(a, b, 4.0, min_cutoff=mn, box=box, method="pkdtree")
+        n = same_pairs(got, oracle.capped_distance(a, b, 4.0, min_cutoff=mn, box=box, method="bruteforce"))
+        assert n > 10000
+        sgot = gd.self_capped_distance(a, 4.0, min_cutoff=mn, box=box, method="bruteforce")
+        same_pairs(sgot, oracle.self_capped_distance(a, 4.0, min_cutoff=mn, box=box, method="bruteforce"), True)
+        assert (sgot[0][:, 0] < sgot[0][:, 1]).all()
+    gridded = gd.capped_distance(a, b, 4.0, box=box, method="bruteforce")
+    monkeypatch.setenv("MDAGPU_NO_BRUTE_GRID", "1")
+    same_pairs(gridded, gd.capped_distance(a, b, 4.0, box=box, method="bruteforce"))
+
+
 def test_capped_distance_edges(oracle):
     from mdanalysis_b200.lib import distances as gd
     e = np.zeros((0, 3), dtype=np.float32)
