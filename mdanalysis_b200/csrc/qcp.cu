@@ -301,38 +301,68 @@ qcp_traj_kernel(const float *traj, uint64_t natoms, const int32_t *__restrict__ 
 // ---------------------------------------------------------------------------
 // TMA-streamed variant (contiguous selection, 16-byte aligned frames)
 // ---------------------------------------------------------------------------
-// Persistent CTAs, one per SM.  One elected thread streams chunks of QS_CH atoms
-// with cp.async.bulk (1-D TMA) into a 2-3 stage shared-memory ring guarded by
-// full/empty mbarriers; 16 warps in 4 groups of 128 threads work on 4
-// frames at once, so the float64 reference chunk (staged once per stage) is
-// shared by 4 frames and its L2 traffic is a quarter of a frame's HBM traffic.
-// No registers are spent on loads in flight: up to ~144 kB per SM are in flight.
-// With `aligned`, the same ring streams the 4 frames a second time (L2-resident:
-// 148 x 4 frames x 120 kB) and the consumers apply the rigid transform.
+// Persistent CTAs, one per SM.  A producer warp streams chunks of QS_CH atoms with
+// cp.async.bulk (1-D TMA) into a shared-memory ring guarded by full/empty mbarriers;
+// 16 consumer warps in QS_FB groups of QS_GT threads work on QS_FB frames at once, so
+// the float64 reference chunk (staged once per stage) is shared by QS_FB frames.
+// No registers are spent on loads in flight.
+//
+// r02 (profiles/r02_ncu_qcp_stream_kernel.txt: issue slots 44 % busy, 1.3 warps per issue
+// waiting at the full barrier, 0.9 at the group barrier): a group is now ONE WARP
+// (QS_GT = 32, 16 frames per batch, chunks of 256 atoms): no barrier among the consumers
+// at all (the 13 sums are reduced by shuffles), the serial Newton solve of 16 frames runs
+// in 16 warps side by side once per 16 frames, the reference chunk is a ninth of a stage
+// instead of a third (more frame bytes in flight), and full chunks take a path without
+// the ragged-quad checks.  Frames are dealt to the CTAs as contiguous, balanced ranges.
+// With `aligned`, the same ring streams the frames a second time (L2-resident) and the
+// consumers apply the rigid transform IN PLACE in the stage, which then leaves through a
+// bulk store (cp.async.bulk shared -> global: full 128-byte lines instead of 16-byte
+// pieces 48 bytes apart); the stage is released one chunk later, when the store has read it.
+#ifndef QS_GT_
+#define QS_GT_ 32
+#endif
 #ifndef QS_CH_
-#define QS_CH_ 1024
+#define QS_CH_ 256
 #endif
 #ifndef QCP_F2D_ALU
 #define QCP_F2D_ALU 0
 #endif
+#ifndef QS_BULK_STORE
+#define QS_BULK_STORE 1
+#endif
 constexpr int QS_CH = QS_CH_;               // atoms per chunk
-constexpr int QS_FB = 4;                    // frames per batch = consumer groups
-constexpr int QS_GT = 128;                  // threads per group
+constexpr int QS_GT = QS_GT_;               // threads per group (one frame)
+constexpr int QS_FB = 512 / QS_GT;          // frames per batch = consumer groups
+constexpr int QS_GW = QS_GT / 32;           // warps per group
+constexpr int QS_QPT = QS_CH / 4 / QS_GT;   // quads per thread and chunk
 constexpr int QS_THREADS = QS_FB * QS_GT;
-constexpr int QS_REF_BYTES = QS_CH * 3 * 8;          // 6 planes x 256 double2
-constexpr int QS_W_BYTES = QS_CH * 8;                // 2 planes x 256 double2
+static_assert(QS_GT == 32 || QS_GT == 64 || QS_GT == 128, "group = 1, 2 or 4 warps");
+static_assert(QS_QPT >= 1 && QS_QPT * 4 * QS_GT == QS_CH, "a chunk is a whole number of quads per thread");
+constexpr int QS_REF_BYTES = QS_CH * 3 * 8;          // 6 planes of double2
+constexpr int QS_W_BYTES = QS_CH * 8;                // 2 planes of double2
 constexpr int QS_FRAME_BYTES = QS_CH * 12;
-// ring depth: as many stages as fit next to ~9 kB of static shared memory in the 227 kB of an SM
+// ring depth: as many stages as fit next to the static shared memory in the 227 kB of an SM
 constexpr int QS_SMEM_BUDGET = 216 * 1024;
 constexpr int QS_STAGES_U = QS_SMEM_BUDGET / (QS_REF_BYTES + QS_FB * QS_FRAME_BYTES);
 constexpr int QS_STAGES_W = QS_SMEM_BUDGET / (QS_REF_BYTES + QS_W_BYTES + QS_FB * QS_FRAME_BYTES);
+static_assert(QS_STAGES_W >= 2, "at least two stages");
 
 __device__ __forceinline__ void group_sync(int group)
 {
-    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(QS_GT) : "memory");
+    if (QS_GT == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(QS_GT) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-// chunked plane layout of the centred reference: for chunk c, plane p (0..5), quad q (0..255)
+// chunked plane layout of the centred reference: for chunk c, plane p (0..5), quad q
 // the double2 {d[2p], d[2p+1]} of the quad's 12 doubles d = {x0 y0 z0 x1 y1 z1 ...};
 // weights: plane p (0..1) holds {w[2p], w[2p+1]} of the quad.  Padding is zero.
 __global__ void __launch_bounds__(256)
@@ -371,74 +401,72 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
 {
     extern __shared__ __align__(128) unsigned char qs_smem[];
     __shared__ uint64_t full_bar[QS_STAGES], empty_bar[QS_STAGES];
-    __shared__ double red[QS_FB][13 * (QS_GT / 32)];
+    __shared__ double red[QS_GW > 1 ? QS_FB : 1][13 * QS_GW];
     __shared__ double s_xf[QS_FB][12];
     constexpr int STAGE_BYTES = QS_REF_BYTES + (WEIGHTED ? QS_W_BYTES : 0) + QS_FB * QS_FRAME_BYTES;
     constexpr int FRAME_OFF = QS_REF_BYTES + (WEIGHTED ? QS_W_BYTES : 0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < QS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], QS_FB * QS_GT / 32); }
+        for (int s = 0; s < QS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], QS_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint64_t nbatch = (p.nframes + QS_FB - 1) / QS_FB;
+    // this CTA's frames: a contiguous range, the ranges differ by at most one frame
+    const uint64_t fbase = p.nframes / gridDim.x, frem = p.nframes % gridDim.x;
+    const uint64_t fr0 = blockIdx.x * fbase + min((uint64_t)blockIdx.x, frem);
+    const uint64_t fr1 = fr0 + fbase + (blockIdx.x < frem ? 1u : 0u);
+    const uint64_t my_batches = (fr1 - fr0 + QS_FB - 1) / QS_FB;
     const uint32_t nchA = (uint32_t)((p.nsel + QS_CH - 1) / QS_CH);
     const uint32_t nchB = p.aligned ? (uint32_t)((p.natoms + QS_CH - 1) / QS_CH) : 0u;
 
-    // ---------------- producer role (lane 0 of warp 0) ----------------
+    // ---------------- producer warp ----------------
     // Chunk number `k` of this CTA (over all its batches and both passes) goes to stage k % STAGES.
+    // After every consumed chunk a warp releases the stage; the producer waits until all consumer
+    // warps have done so and refills it -- no consumer ever blocks on another consumer.
     const uint32_t per_batch = nchA + nchB;
-    const uint64_t my_batches = nbatch > blockIdx.x ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint64_t my_chunks = my_batches * per_batch;
-    auto issue = [&](uint64_t k) {
-        const uint64_t b = blockIdx.x + (k / per_batch) * gridDim.x;
-        const uint32_t c = (uint32_t)(k % per_batch);
-        const uint64_t f0 = b * QS_FB;
-        const int nf = (int)min((uint64_t)QS_FB, p.nframes - f0);
-        const int s = (int)(k % QS_STAGES);
-        unsigned char *st = qs_smem + (size_t)s * STAGE_BYTES;
-        const bool passA = c < nchA;
-        const uint32_t cc = passA ? c : c - nchA;
-        const uint64_t lim = passA ? p.nsel : p.natoms;
-        const uint32_t na = (uint32_t)min((uint64_t)QS_CH, lim - (uint64_t)cc * QS_CH);
-        const uint32_t fbytes = ((na + 3u) & ~3u) * 12u;
-        uint32_t bytes = (uint32_t)nf * fbytes;
-        if (passA) bytes += QS_REF_BYTES + (WEIGHTED ? QS_W_BYTES : 0);
-        mbar_expect_tx(&full_bar[s], bytes);
-        if (passA) {
-            bulk_g2s(st, p.refp + (uint64_t)cc * 6 * (QS_CH / 4), QS_REF_BYTES, &full_bar[s]);
-            if (WEIGHTED) bulk_g2s(st + QS_REF_BYTES, p.wp + (uint64_t)cc * 2 * (QS_CH / 4), QS_W_BYTES, &full_bar[s]);
-        }
-        for (int g = 0; g < nf; ++g)
-            bulk_g2s(st + FRAME_OFF + g * QS_FRAME_BYTES, p.traj + ((f0 + g) * p.natoms + (uint64_t)cc * QS_CH) * 3,
-                     fbytes, &full_bar[s]);
-    };
-    // after every consumed chunk a warp releases the stage; the PRODUCER WARP (the extra, 17th
-    // warp) waits until all consumer warps have done so and refills it -- no consumer ever
-    // blocks on another consumer (with a consumer doing the refills its own group fell behind
-    // by one chunk per stage and everybody queued up behind it)
-    auto release_and_refill = [&](uint32_t k) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[k % QS_STAGES]);
-    };
     if (warp == QS_THREADS / 32) {
-        if (lane == 0) {
-            for (uint64_t k = 0; k < my_chunks; ++k) {
-                if (k >= QS_STAGES) mbar_wait(&empty_bar[k % QS_STAGES], ((k - QS_STAGES) / QS_STAGES) & 1u);
-                issue(k);
+        // lane g issues the copy of frame g, lane QS_FB the reference chunk (one thread issuing all
+        // 17 copies of a stage spent ~55 ns on each: profiles/microbench/qcp_variants_b200.txt)
+        const uint64_t my_chunks = my_batches * per_batch;
+        uint64_t f0 = fr0;
+        uint32_t c = 0;
+        for (uint64_t k = 0; k < my_chunks; ++k) {
+            const int s = (int)(k % QS_STAGES);
+            if (k >= QS_STAGES) mbar_wait(&empty_bar[s], ((k - QS_STAGES) / QS_STAGES) & 1u);
+            const int nf = (int)min((uint64_t)QS_FB, fr1 - f0);
+            unsigned char *st = qs_smem + (size_t)s * STAGE_BYTES;
+            const bool passA = c < nchA;
+            const uint32_t cc = passA ? c : c - nchA;
+            const uint64_t lim = passA ? p.nsel : p.natoms;
+            const uint32_t na = (uint32_t)min((uint64_t)QS_CH, lim - (uint64_t)cc * QS_CH);
+            const uint32_t fbytes = ((na + 3u) & ~3u) * 12u;
+            if (lane == 0) {
+                uint32_t bytes = (uint32_t)nf * fbytes;
+                if (passA) bytes += QS_REF_BYTES + (WEIGHTED ? QS_W_BYTES : 0);
+                mbar_expect_tx(&full_bar[s], bytes);
             }
+            __syncwarp();
+            if (lane == QS_FB && passA) {
+                bulk_g2s(st, p.refp + (uint64_t)cc * 6 * (QS_CH / 4), QS_REF_BYTES, &full_bar[s]);
+                if (WEIGHTED) bulk_g2s(st + QS_REF_BYTES, p.wp + (uint64_t)cc * 2 * (QS_CH / 4), QS_W_BYTES, &full_bar[s]);
+            }
+            if (lane < nf)
+                bulk_g2s(st + FRAME_OFF + lane * QS_FRAME_BYTES, p.traj + ((f0 + lane) * p.natoms + (uint64_t)cc * QS_CH) * 3,
+                         fbytes, &full_bar[s]);
+            if (++c == per_batch) { c = 0; f0 += QS_FB; }
         }
         return;
     }
 
     // ---------------- consumers ----------------
-    const int g = warp / (QS_GT / 32), gt = tid % QS_GT;
+    const int g = warp / QS_GW, gt = tid % QS_GT;
     const double W = p.refinfo->wsum;
     const double rx = p.refinfo->com[0], ry = p.refinfo->com[1], rz = p.refinfo->com[2];
     uint32_t it = 0;
-    for (uint64_t b = blockIdx.x; b < nbatch; b += gridDim.x) {
-        const uint64_t f = b * QS_FB + g;
-        const bool active = f < p.nframes;
+    int pending = -1;                                   // stage whose bulk store has not been waited for (thread gt == 0)
+    for (uint64_t b = 0; b < my_batches; ++b) {
+        const uint64_t f = fr0 + b * QS_FB + g;
+        const bool active = f < fr1;
         double acc[13];
 #pragma unroll
         for (int k = 0; k < 13; ++k) acc[k] = 0.0;
@@ -456,12 +484,9 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
                     px = (double)first.x; py = (double)first.y; pz = (double)first.z;
                 }
                 const uint32_t na = (uint32_t)min((uint64_t)QS_CH, p.nsel - (uint64_t)c * QS_CH);
-#pragma unroll
-                for (int h = 0; h < QS_CH / 4 / QS_GT; ++h) {
-                    const uint32_t q = gt + h * QS_GT;
-                    if (q * 4 >= na) break;
+                auto quad = [&](uint32_t q, bool ragged) {
                     float4 v0 = fr4[3 * q], v1 = fr4[3 * q + 1], v2 = fr4[3 * q + 2];
-                    if (q * 4 + 4 > na) {       // ragged last quad: atoms past the selection count as the pivot (zero y')
+                    if (ragged && q * 4 + 4 > na) {     // last quad: atoms past the selection count as the pivot (zero y')
                         const float fx = (float)px, fy = (float)py, fz = (float)pz;
                         if (q * 4 + 1 >= na) { v0.w = fx; v1.x = fy; v1.y = fz; }
                         if (q * 4 + 2 >= na) { v1.z = fx; v1.w = fy; v2.x = fz; }
@@ -478,26 +503,43 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
                     qcp_accumulate<WEIGHTED>(acc, v0.w, v1.x, v1.y, px, py, pz, r1.y, r2.x, r2.y, w1);
                     qcp_accumulate<WEIGHTED>(acc, v1.z, v1.w, v2.x, px, py, pz, r3.x, r3.y, r4.x, w2);
                     qcp_accumulate<WEIGHTED>(acc, v2.y, v2.z, v2.w, px, py, pz, r4.y, r5.x, r5.y, w3);
-                }
-            }
-            release_and_refill(it);
-        }
-        // ---- group reduction (4 warps) and solve ------------------------------------------
-        {
-            const int gw = (tid % QS_GT) >> 5;
+                };
+                if (na == (uint32_t)QS_CH) {
 #pragma unroll
-            for (int k = 0; k < 13; ++k) {
-                const double v = warp_sum(acc[k]);
-                if (lane == 0) red[g][k * (QS_GT / 32) + gw] = v;
-            }
-            group_sync(g);
-            if (gt == 0 && active) {
-                double sum[13];
-                for (int k = 0; k < 13; ++k) {
-                    double v = 0.0;
-                    for (int w4 = 0; w4 < QS_GT / 32; ++w4) v += red[g][k * (QS_GT / 32) + w4];
-                    sum[k] = v;
+                    for (int h = 0; h < QS_QPT; ++h) quad(gt + h * QS_GT, false);
+                } else {
+                    for (int h = 0; h < QS_QPT; ++h) {
+                        const uint32_t q = gt + h * QS_GT;
+                        if (q * 4 >= na) break;
+                        quad(q, true);
+                    }
                 }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+        // ---- group reduction and solve ------------------------------------------------------
+        {
+            double sum[13];
+            if (QS_GW == 1) {
+#pragma unroll
+                for (int k = 0; k < 13; ++k) sum[k] = warp_sum(acc[k]);
+            } else {
+                const int gw = (tid % QS_GT) >> 5;
+#pragma unroll
+                for (int k = 0; k < 13; ++k) {
+                    const double v = warp_sum(acc[k]);
+                    if (lane == 0) red[QS_GW > 1 ? g : 0][k * QS_GW + gw] = v;
+                }
+                group_sync(g);
+                if (gt == 0)
+                    for (int k = 0; k < 13; ++k) {
+                        double v = 0.0;
+                        for (int w4 = 0; w4 < QS_GW; ++w4) v += red[QS_GW > 1 ? g : 0][k * QS_GW + w4];
+                        sum[k] = v;
+                    }
+            }
+            if (gt == 0 && active) {
                 const double m0 = sum[10] / W, m1 = sum[11] / W, m2 = sum[12] / W;
                 const double mx = px + m0, my = py + m1, mz = pz + m2;
                 const double sx[3] = { p.refinfo->sx[0], p.refinfo->sx[1], p.refinfo->sx[2] };
@@ -566,13 +608,14 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
         for (uint32_t c = 0; c < nchB; ++c, ++it) {
             const int s = it % QS_STAGES;
             mbar_wait(&full_bar[s], (it / QS_STAGES) & 1u);
+            unsigned char *st = qs_smem + (size_t)s * STAGE_BYTES;
+            float4 *fr4 = reinterpret_cast<float4 *>(st + FRAME_OFF + g * QS_FRAME_BYTES);
+            float *gdst = p.aligned + (f * p.natoms + (uint64_t)c * QS_CH) * 3;
+            const uint32_t na = (uint32_t)min((uint64_t)QS_CH, p.natoms - (uint64_t)c * QS_CH);   // multiple of 4
             if (active) {
-                const unsigned char *st = qs_smem + (size_t)s * STAGE_BYTES;
-                const float4 *fr4 = reinterpret_cast<const float4 *>(st + FRAME_OFF + g * QS_FRAME_BYTES);
-                float4 *dst4 = reinterpret_cast<float4 *>(p.aligned + (f * p.natoms + (uint64_t)c * QS_CH) * 3);
-                const uint32_t na = (uint32_t)min((uint64_t)QS_CH, p.natoms - (uint64_t)c * QS_CH);   // multiple of 4
+                float4 *dst4 = QS_BULK_STORE ? fr4 : reinterpret_cast<float4 *>(gdst);
 #pragma unroll
-                for (int h = 0; h < QS_CH / 4 / QS_GT; ++h) {
+                for (int h = 0; h < QS_QPT; ++h) {
                     const uint32_t q = gt + h * QS_GT;
                     if (q * 4 >= na) break;
                     const float4 v0 = fr4[3 * q], v1 = fr4[3 * q + 1], v2 = fr4[3 * q + 2];
@@ -584,9 +627,31 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
                     dst4[3 * q] = o0; dst4[3 * q + 1] = o1; dst4[3 * q + 2] = o2;
                 }
             }
-            release_and_refill(it);
+            if (QS_BULK_STORE) {
+                // the transformed chunk leaves through the async proxy; the stage is handed back one
+                // chunk later, when that store has read it
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                group_sync(g);
+                if (gt == 0) {
+                    if (pending >= 0) {
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_arrive_n(&empty_bar[pending], QS_GW);
+                    }
+                    if (active) bulk_s2g(gdst, fr4, na * 12u);
+                    pending = s;
+                }
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+            }
+        }
+        if (QS_BULK_STORE && gt == 0 && pending >= 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive_n(&empty_bar[pending], QS_GW);
+            pending = -1;
         }
     }
+    if (QS_BULK_STORE && gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // single pair of already-centred float64 structures (CalcRMSDRotationalMatrix)
@@ -761,9 +826,10 @@ extern "C" int mdagpu_qcp_trajectory(const float *traj, uint64_t nframes, uint64
         qp.refc = refc.as<double>(); qp.refp = refp.as<double2>(); qp.wp = weights ? wp.as<double2>() : nullptr;
         qp.refinfo = info.as<RefInfo>(); qp.rmsd_out = rm.as<double>(); qp.rot_out = rot ? ro.as<double>() : nullptr;
         qp.aligned = aligned ? al.as<float>() : nullptr; qp.convention = convention; qp.allclose_shortcut = allclose_shortcut;
+        // one CTA per SM, each with a contiguous range of >= QS_FB frames (fewer CTAs for short trajectories)
         const uint64_t nbatch = (nframes + QS_FB - 1) / QS_FB;
         const unsigned grid = (unsigned)(nbatch < (uint64_t)num_sms() ? nbatch : (uint64_t)num_sms());
-        // ring depth: as many stages as fit in the 227 kB of one SM (3 x 72 kB, or 2 x 80 kB with weights)
+        // ring depth: as many stages as fit in the 227 kB of one SM
         constexpr int SW = QS_STAGES_W, SU = QS_STAGES_U;
         if (weights) {
             const size_t smem = SW * (size_t)(QS_REF_BYTES + QS_W_BYTES + QS_FB * QS_FRAME_BYTES);

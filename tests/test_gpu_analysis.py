@@ -261,11 +261,12 @@ def test_self_contacts(oracle):
     assert contact_matrix(np.array([1.0, 8.0, 8.1]), 8.0).tolist() == [True, True, False]
 
 
-@pytest.mark.parametrize("n,F", [(2048, 5), (4100, 9), (10000, 3)])
+@pytest.mark.parametrize("n,F", [(2048, 5), (4100, 9), (10000, 3), (2048, 700), (2304, 2500)])
 @pytest.mark.parametrize("weighted", [False, True])
 def test_qcp_trajectory_streamed_kernel(oracle, n, F, weighted):
     """natoms % 4 == 0 and >= 2048 fitted atoms: the TMA-streamed persistent kernel (qcp.cu,
-    qcp_stream_kernel), incl. ragged last chunk, partial last batch of 4 frames, in-place alignment."""
+    qcp_stream_kernel), incl. ragged last chunk, partial batches of frames (one batch in one CTA; 44 CTAs
+    with 15 or 16 frames; 148 CTAs with a full batch and a batch of one frame), in-place alignment."""
     import torch
     from mdanalysis_b200.lib import qcprot
     rng = np.random.default_rng(n + F)
