@@ -7,22 +7,22 @@
 //                                                     -> convention 1
 //   core/groups.py:1083-1106 center(), :1478-1529 translate()/rotate()
 //
-// One CTA per frame, several CTAs per SM.  Every frame is read from HBM exactly
-// once, with 16-byte loads where the layout allows (natoms % 4 == 0, contiguous
-// selection): a thread owns "quads" of 4 atoms = 3 float4.  A single pass
-// accumulates, in float64 and relative to a per-frame pivot (the first fitted atom,
-// which removes the translation from the magnitudes that are summed),
+// Two kernels.  qcp_traj_kernel (index lists, small or unaligned selections): one CTA per
+// frame, several CTAs per SM, 16-byte loads where the layout allows.  qcp_stream_kernel (the
+// C4 path: contiguous selections of >= 2048 atoms): persistent CTAs, one WARP per frame, the
+// frames of a batch streamed through a TMA ring next to the float64 reference chunk they share.
+// Both read every frame from HBM once and accumulate in a single pass, in float64 and
+// relative to a per-frame pivot (the first fitted atom, which removes the translation from
+// the magnitudes that are summed),
 //     Sy = sum w y',  M = sum w y' (x - x_com)^T,  G = sum w |y'|^2 ,   y' = y - pivot
 // from which the centred quantities the reference forms (it centres in float64
 // before calling QCP, rms.py:685-701) follow exactly:
 //     y_com = pivot + Sy/W,  A = M - (Sy/W) (sum w (x - x_com))^T,  G1 = G - |Sy|^2/W.
 // The centred (and weight-scaled) reference is prepared once per call in float64
-// (qcp_ref_kernel) and is read through L1/L2 by every CTA.  A warp shuffle +
-// shared-memory tree reduces the 13 sums; one thread runs the Newton-Raphson quartic
-// solve and the adjugate/quaternion step (geom.cuh qcp_solve) while the other CTAs
-// of the SM keep streaming.  With `aligned`, the CTA re-reads its frame (still in
-// L2: at most a few frames per SM are in flight) and applies the rigid transform
-// to every atom with the reference's three float32 roundings.
+// (qcp_ref_kernel).  One thread per frame runs the Newton-Raphson quartic solve and the
+// adjugate/quaternion step (geom.cuh qcp_solve).  With `aligned`, the frame is read a second
+// time and every atom gets translate(-com), rotate(R), translate(+ref_com), each rounded to
+// float32 as the reference's in-place float32 positions are (core/groups.py:1480, 1527).
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -356,10 +356,73 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+// L2 policies for the AlignTraj pass (QS_L2_HINTS, off): evict_last on the loads of the first pass and
+// evict_first on the second-pass loads and the stores were meant to keep the frames in L2 between
+// the passes.  Measured: no effect at 4, 8 or 16 frames per CTA (3.35 / 2.97 / 3.00 ms with and
+// without, profiles/microbench/qcp_variants_b200.txt) -- the second pass re-reads from HBM either
+// way, the pass moves 36 B per atom and runs at 6.1 TB/s of DRAM traffic.
+#ifndef QS_L2_HINTS
+#define QS_L2_HINTS 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
 {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes, uint64_t pol)
+{
+    if (QS_L2_HINTS)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     ::"l"(dst), "r"(smem_u32(src)), "r"(bytes), "l"(pol) : "memory");
+    else
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// fl32(x + t) for a float32 x and a float64 t = th + tl (th = fl32(t), tl = fl32(t - th)), two
+// coordinates at a time, without leaving the FP32 pipe: Knuth's TwoSum gives x + th = s + e exactly,
+// the result is fl32(s + fl32(e + tl)).  This is the float64 sum rounded once to float32 -- what
+// `positions += vector` does (core/groups.py:1480) -- unless the exact value lies within ~2^-23 ulp of
+// a rounding midpoint (about one coordinate in 10^7; it is then the neighbouring float32).  The
+// float64 version cost nine conversions per atom on the quarter-rate XU pipe, which bounded the
+// AlignTraj pass (profiles/r02b_ncu_qcp_align.txt: XU 61 % over both passes).
+#ifndef QCP_DF_TRANSLATE
+#define QCP_DF_TRANSLATE 1
+#endif
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 df_translate2(float2 x, float2 th, float2 tl)
+{
+    const float2 s = __fadd2_rn(x, th);
+    const float2 bb = __fadd2_rn(s, neg2(x));
+    const float2 t1 = __fadd2_rn(s, neg2(bb));
+    const float2 t2 = __fadd2_rn(x, neg2(t1));
+    const float2 t3 = __fadd2_rn(th, neg2(bb));
+    const float2 e = __fadd2_rn(t2, t3);
+    const float2 r = __fadd2_rn(e, tl);
+    return __fadd2_rn(s, r);
+}
+struct DFShift { float2 xy_h, xy_l, zx_h, zx_l, yz_h, yz_l; };
+__device__ __forceinline__ DFShift df_shift(double tx, double ty, double tz)
+{
+    const float hx = (float)tx, hy = (float)ty, hz = (float)tz;
+    const float lx = (float)(tx - (double)hx), ly = (float)(ty - (double)hy), lz = (float)(tz - (double)hz);
+    DFShift d;
+    d.xy_h = make_float2(hx, hy); d.xy_l = make_float2(lx, ly);
+    d.zx_h = make_float2(hz, hx); d.zx_l = make_float2(lz, lx);
+    d.yz_h = make_float2(hy, hz); d.yz_l = make_float2(ly, lz);
+    return d;
 }
 
 // chunked plane layout of the centred reference: for chunk c, plane p (0..5), quad q
@@ -428,6 +491,7 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
         // lane g issues the copy of frame g, lane QS_FB the reference chunk (one thread issuing all
         // 17 copies of a stage spent ~55 ns on each: profiles/microbench/qcp_variants_b200.txt)
         const uint64_t my_chunks = my_batches * per_batch;
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
         uint64_t f0 = fr0;
         uint32_t c = 0;
         for (uint64_t k = 0; k < my_chunks; ++k) {
@@ -450,9 +514,12 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
                 bulk_g2s(st, p.refp + (uint64_t)cc * 6 * (QS_CH / 4), QS_REF_BYTES, &full_bar[s]);
                 if (WEIGHTED) bulk_g2s(st + QS_REF_BYTES, p.wp + (uint64_t)cc * 2 * (QS_CH / 4), QS_W_BYTES, &full_bar[s]);
             }
-            if (lane < nf)
-                bulk_g2s(st + FRAME_OFF + lane * QS_FRAME_BYTES, p.traj + ((f0 + lane) * p.natoms + (uint64_t)cc * QS_CH) * 3,
-                         fbytes, &full_bar[s]);
+            if (lane < nf) {
+                unsigned char *dst = st + FRAME_OFF + lane * QS_FRAME_BYTES;
+                const float *src = p.traj + ((f0 + lane) * p.natoms + (uint64_t)cc * QS_CH) * 3;
+                if (QS_L2_HINTS && nchB) bulk_g2s_hint(dst, src, fbytes, &full_bar[s], passA ? pol_keep : pol_stream);
+                else bulk_g2s(dst, src, fbytes, &full_bar[s]);
+            }
             if (++c == per_batch) { c = 0; f0 += QS_FB; }
         }
         return;
@@ -463,6 +530,7 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
     const double W = p.refinfo->wsum;
     const double rx = p.refinfo->com[0], ry = p.refinfo->com[1], rz = p.refinfo->com[2];
     uint32_t it = 0;
+    const uint64_t pol_out = l2_policy_evict_first();
     int pending = -1;                                   // stage whose bulk store has not been waited for (thread gt == 0)
     for (uint64_t b = 0; b < my_batches; ++b) {
         const uint64_t f = fr0 + b * QS_FB + g;
@@ -592,6 +660,41 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
         double R[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) R[k] = s_xf[g][k];
+#if QCP_DF_TRANSLATE
+        // The two translations as float32 "double-float" sums (see df_translate2): t = -com and
+        // t = +ref_com, each split into hi + lo, paired the way the coordinates of a quad pair up
+        // ({x y} {z x} {y z}).  The rotation stays in float64.
+        const DFShift sub = df_shift(-s_xf[g][9], -s_xf[g][10], -s_xf[g][11]);
+        const DFShift add = df_shift(rx, ry, rz);
+        auto rotate = [&](float p0, float p1, float p2, float &r0, float &r1, float &r2) {
+            const double d0 = (double)p0, d1 = (double)p1, d2 = (double)p2;
+            r0 = (float)fma(d2, R[6], fma(d1, R[3], d0 * R[0]));
+            r1 = (float)fma(d2, R[7], fma(d1, R[4], d0 * R[1]));
+            r2 = (float)fma(d2, R[8], fma(d1, R[5], d0 * R[2]));
+        };
+        auto move_quad = [&](float4 &v0, float4 &v1, float4 &v2) {
+            float2 a = df_translate2(make_float2(v0.x, v0.y), sub.xy_h, sub.xy_l);
+            float2 b = df_translate2(make_float2(v0.z, v0.w), sub.zx_h, sub.zx_l);
+            float2 c = df_translate2(make_float2(v1.x, v1.y), sub.yz_h, sub.yz_l);
+            float2 d = df_translate2(make_float2(v1.z, v1.w), sub.xy_h, sub.xy_l);
+            float2 e = df_translate2(make_float2(v2.x, v2.y), sub.zx_h, sub.zx_l);
+            float2 f2 = df_translate2(make_float2(v2.z, v2.w), sub.yz_h, sub.yz_l);
+            float4 r0, r1, r2;
+            rotate(a.x, a.y, b.x, r0.x, r0.y, r0.z);
+            rotate(b.y, c.x, c.y, r0.w, r1.x, r1.y);
+            rotate(d.x, d.y, e.x, r1.z, r1.w, r2.x);
+            rotate(e.y, f2.x, f2.y, r2.y, r2.z, r2.w);
+            a = df_translate2(make_float2(r0.x, r0.y), add.xy_h, add.xy_l);
+            b = df_translate2(make_float2(r0.z, r0.w), add.zx_h, add.zx_l);
+            c = df_translate2(make_float2(r1.x, r1.y), add.yz_h, add.yz_l);
+            d = df_translate2(make_float2(r1.z, r1.w), add.xy_h, add.xy_l);
+            e = df_translate2(make_float2(r2.x, r2.y), add.zx_h, add.zx_l);
+            f2 = df_translate2(make_float2(r2.z, r2.w), add.yz_h, add.yz_l);
+            v0 = make_float4(a.x, a.y, b.x, b.y);
+            v1 = make_float4(c.x, c.y, d.x, d.y);
+            v2 = make_float4(e.x, e.y, f2.x, f2.y);
+        };
+#else
         const double cx = s_xf[g][9], cy = s_xf[g][10], cz = s_xf[g][11];
         auto move = [&](float x, float y, float z, float &ox, float &oy, float &oz) {
             const float p0 = (float)(f2d_alu(x) - cx);
@@ -605,6 +708,15 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
             oy = (float)(f2d_alu(r1) + ry);
             oz = (float)(f2d_alu(r2) + rz);
         };
+        auto move_quad = [&](float4 &v0, float4 &v1, float4 &v2) {
+            float4 o0, o1, o2;
+            move(v0.x, v0.y, v0.z, o0.x, o0.y, o0.z);
+            move(v0.w, v1.x, v1.y, o0.w, o1.x, o1.y);
+            move(v1.z, v1.w, v2.x, o1.z, o1.w, o2.x);
+            move(v2.y, v2.z, v2.w, o2.y, o2.z, o2.w);
+            v0 = o0; v1 = o1; v2 = o2;
+        };
+#endif
         for (uint32_t c = 0; c < nchB; ++c, ++it) {
             const int s = it % QS_STAGES;
             mbar_wait(&full_bar[s], (it / QS_STAGES) & 1u);
@@ -618,13 +730,9 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
                 for (int h = 0; h < QS_QPT; ++h) {
                     const uint32_t q = gt + h * QS_GT;
                     if (q * 4 >= na) break;
-                    const float4 v0 = fr4[3 * q], v1 = fr4[3 * q + 1], v2 = fr4[3 * q + 2];
-                    float4 o0, o1, o2;
-                    move(v0.x, v0.y, v0.z, o0.x, o0.y, o0.z);
-                    move(v0.w, v1.x, v1.y, o0.w, o1.x, o1.y);
-                    move(v1.z, v1.w, v2.x, o1.z, o1.w, o2.x);
-                    move(v2.y, v2.z, v2.w, o2.y, o2.z, o2.w);
-                    dst4[3 * q] = o0; dst4[3 * q + 1] = o1; dst4[3 * q + 2] = o2;
+                    float4 v0 = fr4[3 * q], v1 = fr4[3 * q + 1], v2 = fr4[3 * q + 2];
+                    move_quad(v0, v1, v2);
+                    dst4[3 * q] = v0; dst4[3 * q + 1] = v1; dst4[3 * q + 2] = v2;
                 }
             }
             if (QS_BULK_STORE) {
@@ -637,7 +745,7 @@ __global__ void __launch_bounds__(QS_THREADS + 32, 1) qcp_stream_kernel(const Qc
                         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                         mbar_arrive_n(&empty_bar[pending], QS_GW);
                     }
-                    if (active) bulk_s2g(gdst, fr4, na * 12u);
+                    if (active) bulk_s2g(gdst, fr4, na * 12u, pol_out);
                     pending = s;
                 }
             } else {
