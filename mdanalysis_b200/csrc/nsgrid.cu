@@ -264,6 +264,7 @@ struct PairTraversal {
     int row = 0;
     RowParams rp = { 1, 1 };
     uint64_t grid_x = 0;
+    int cap = RP_ALL;          // plane capacity of the row kernel (candidates): sizes its shared memory
 };
 
 static PairTraversal choose_traversal(int mic, const FrameGeom &fg, double cutoff, uint64_t n_queries, bool consistent)
@@ -281,6 +282,16 @@ static PairTraversal choose_traversal(int mic, const FrameGeom &fg, double cutof
     tv.rp.R = (nx + runs - 1) / runs;
     tv.grid_x = (uint64_t)runs * (uint64_t)fg.grid.ncells[1] * (uint64_t)fg.grid.ncells[2];
     tv.row = 1;
+    // Tile capacity: the CTA stages (2W + 1)^2 rows (the half shell of a self search: the home row and
+    // W + (2W + 1) W more) of R + 2W cells; 1.5 x the mean leaves room for the spread of the cell
+    // occupancies (a CTA whose rows do not fit stages them one at a time).  The resident CTAs per SM
+    // follow from this number: 1 M atoms at 0.1 / A^3, 8 A: 1856 candidates = 22 kB (the fixed 43 kB
+    // allowed 4 CTAs of 4 warps).
+    const double rows = (double)((2 * tv.rp.W + 1) * (2 * tv.rp.W + 1));
+    const double mean = rows * (double)(tv.rp.R + 2 * tv.rp.W) * occupancy;
+    int cap = (int)(1.5 * mean) + 64;
+    cap = (cap + 63) & ~63;
+    tv.cap = cap < RP_MINCAP ? RP_MINCAP : (cap > RP_ALL ? RP_ALL : cap);
     return tv;
 }
 
@@ -303,9 +314,12 @@ static int run_pair_search(const CellList &ql, uint64_t nq, const CellList &cl,
         PairSink sink = { res->pairs, res->dist, counter.as<unsigned long long>(), cap, orient };
         if constexpr (MIC != MIC_ORTHO_ROUND) if (tv.row) {
             dim3 grid((unsigned)tv.grid_x, 1);
-            MDA_CUDA(cudaFuncSetAttribute(row_pairs_kernel<MIC, SELF, PairSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_DYN_BYTES));
-            MDA_LAUNCH_AS(SELF ? "pair_self_search" : "pair_search", (row_pairs_kernel<MIC, SELF, PairSink>), grid, PairSink::THREADS, RP_DYN_BYTES, st,
-                       ql.atoms(), ql.start(), cl.atoms(), cl.start(), fg_dev, 0, tv.rp, sp, sink);
+            // (a self search stages the half shell, about half of what tv.cap was sized for: the same
+            // number is used for both so that one attribute setting serves the kernel)
+            const int cap = SELF ? (((tv.cap * 5 / 9 + 63) & ~63) < RP_MINCAP ? RP_MINCAP : ((tv.cap * 5 / 9 + 63) & ~63)) : tv.cap;
+            MDA_CUDA(cudaFuncSetAttribute(row_pairs_kernel<MIC, SELF, PairSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp_dyn_bytes(RP_ALL)));
+            MDA_LAUNCH_AS(SELF ? "pair_self_search" : "pair_search", (row_pairs_kernel<MIC, SELF, PairSink>), grid, RP_THREADS, rp_dyn_bytes(cap), st,
+                       ql.atoms(), ql.start(), cl.atoms(), cl.start(), fg_dev, 0, tv.rp, sp, sink, cap);
         }
         if (!tv.row || MIC == MIC_ORTHO_ROUND) {
             dim3 grid(cdiv(nq, PairSink::THREADS), 1);

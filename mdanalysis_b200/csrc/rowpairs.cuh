@@ -14,6 +14,14 @@
 //   * whenever 32 are queued, all 32 lanes evaluate one each with the reference's float64
 //     arithmetic (the image predicted for the cell pair, geom.cuh) and append the accepted
 //     ones through the sink (warp-aggregated global atomic, engine.cuh PairSink).
+// r02 (plane path).  ncu of the ballot-compacting walk (profiles/r02_ncu_fastns_row_pairs_kernel.txt): 38
+// thread-instructions per candidate, of which the compaction (ballot, popc, three stores, queue
+// bookkeeping -- executed for nearly every candidate, a warp of 32 queries almost always has a
+// survivor) cost as much as the filter.  Now every lane keeps its OWN survivors (a predicated
+// 2-byte store and an add per candidate, [slot][lane] layout), the filter arithmetic is packed
+// (FADD2 / FFMA2: two candidates per issue slot), and when a lane's queue is nearly full the
+// warp evaluates the queued pairs two per lane and round -- each lane its own, so the query
+// stays in registers (no shuffles) and the image code comes from the entry's row.
 // Staging.  When all stencil rows of the CTA fit (RP_ALL candidates; 1 M atoms at 0.1 / A^3 and an
 // 8 A cutoff: 14 rows x ~234), they are staged ONCE as x / y / z planes and every warp then
 // runs through its rows on its own: with one __syncthreads per row the warps that had just
@@ -29,25 +37,35 @@ namespace mdagpu {
 constexpr int RP_TILE = 1024;             // staged candidates per buffer (row-by-row path)
 constexpr int RP_ALL = 3584;              // staged candidates of ALL rows (plane path): 3 x 14 kB
 constexpr int RP_QUEUE = 96;              // queued survivors per warp (drained at >= 32)
-constexpr int RP_NQ = 1;                  // quads of candidates per trip of the plane path (2: spills, 3.2 -> 3.5 ms)
-constexpr int RP_PAD = 4 * RP_NQ;         // sentinels behind the last row (a trip may read past the end)
-constexpr size_t RP_DYN_BYTES = 3 * (RP_ALL + RP_PAD) * sizeof(float);   // >= 2 * RP_TILE * sizeof(float4)
-static_assert(RP_DYN_BYTES >= 2 * RP_TILE * sizeof(float4), "the row-by-row buffers live in the same allocation");
+constexpr int RP_PAD = 4;                 // sentinels behind the last row (a trip may read past the end)
+constexpr int RP_THREADS = 192;           // 6 warps: the 3 chunks x 2 row parts of a ~80-query home cell, one item each
+constexpr int RP_LQ = 24;                 // survivors a lane can hold between two drains
+constexpr int RP_WQ = 128;                // compacted warp queue (evaluated 64 at a time)
+constexpr int RP_PARTROWS = 16;           // rows per work item (4 bits of a queue entry)
+// dynamic shared memory for a plane capacity of `cap` candidates (a multiple of 4, <= RP_ALL); the two
+// buffers of the row-by-row path live in the same allocation (cap * 12 / 32 candidates each)
+__host__ __device__ constexpr size_t rp_dyn_bytes(int cap) { return 3 * (size_t)(cap + RP_PAD) * sizeof(float); }
+constexpr int RP_MINCAP = 512;
 
-template <int MIC, bool SELF, class Sink>
-__global__ void __launch_bounds__(Sink::THREADS)
+template <int MIC, bool SELF, class Sink, int T_ = RP_THREADS>
+__global__ void __launch_bounds__(T_)
 row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
                  const float4 *__restrict__ c_atoms, const uint32_t *__restrict__ c_start,
-                 const FrameGeom *__restrict__ fgs, int per_frame, RowParams rp, SearchParams sp, Sink sink)
+                 const FrameGeom *__restrict__ fgs, int per_frame, RowParams rp, SearchParams sp, Sink sink, int cap)
 {
-    constexpr int T = Sink::THREADS, NW = T / 32;
+    constexpr int T = T_, NW = T / 32;
     __shared__ RowBook bk;
-    extern __shared__ __align__(16) unsigned char rp_dyn[];         // RP_DYN_BYTES
-    float4 (*tile)[RP_TILE] = reinterpret_cast<float4 (*)[RP_TILE]>(rp_dyn);
+    extern __shared__ __align__(16) unsigned char rp_dyn[];         // rp_dyn_bytes(cap)
+    const uint32_t rtile = (uint32_t)(rp_dyn_bytes(cap) / (2 * sizeof(float4)));   // candidates per buffer, row-by-row path
+    float4 *tile0 = reinterpret_cast<float4 *>(rp_dyn);
     __shared__ uint32_t s_rowbase[ROW_MAXROWS + 1];
     __shared__ uint32_t s_next;                                     // next unclaimed work item (plane path)
-    __shared__ uint32_t s_qq[NW][RP_QUEUE], s_qc[NW][RP_QUEUE];
-    __shared__ uint8_t s_qi[NW][RP_QUEUE];
+    // plane path: per-lane survivor queues [warp][slot][lane]; row-by-row path: per-warp compacted queues
+    constexpr int Q_PLANE = NW * (RP_LQ * 32 * 2 + RP_WQ * 4), Q_ROW = NW * RP_QUEUE * 9;
+    __shared__ __align__(16) unsigned char s_queue[Q_PLANE > Q_ROW ? Q_PLANE : Q_ROW];
+    uint32_t (*s_qq)[RP_QUEUE] = reinterpret_cast<uint32_t (*)[RP_QUEUE]>(s_queue);
+    uint32_t (*s_qc)[RP_QUEUE] = reinterpret_cast<uint32_t (*)[RP_QUEUE]>(s_queue + NW * RP_QUEUE * 4);
+    uint8_t (*s_qi)[RP_QUEUE] = reinterpret_cast<uint8_t (*)[RP_QUEUE]>(s_queue + NW * RP_QUEUE * 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t f = blockIdx.y;
     sink.begin();
@@ -90,17 +108,17 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
         __syncwarp();
     };
 
-    // stage (row r, offset p .. p + RP_TILE) into buffer b: all threads, coalesced 16-byte loads
+    // stage (row r, offset p .. p + rtile) into buffer b: all threads, coalesced 16-byte loads
     auto stage = [&](int r, uint32_t p, int b) {
         const RowInfo &ri = bk.row[r];
-        const uint32_t pe = min(p + (uint32_t)RP_TILE, ri.end[2]);
+        const uint32_t pe = min(p + rtile, ri.end[2]);
         for (uint32_t t = p + tid; t < pe; t += T) {
             const int s = t >= ri.end[1] ? 2 : (t >= ri.end[0] ? 1 : 0);
-            tile[b][t - p] = c_atoms[ri.g[s] + (t - (s ? ri.end[s - 1] : 0u))];
+            tile0[(uint32_t)b * rtile + (t - p)] = c_atoms[ri.g[s] + (t - (s ? ri.end[s - 1] : 0u))];
         }
     };
     auto next_stage = [&](int &r, uint32_t &p) {
-        p += RP_TILE;
+        p += rtile;
         if (p >= bk.row[r].end[2]) {
             p = 0;
             do { ++r; } while (r < nrows && bk.row[r].end[2] == 0u);
@@ -114,8 +132,8 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
         s_rowbase[nrows] = b0;
     }
     __syncthreads();
-    if (s_rowbase[nrows] <= (uint32_t)RP_ALL) {
-        float *px = reinterpret_cast<float *>(rp_dyn), *py = px + (RP_ALL + RP_PAD), *pz = py + (RP_ALL + RP_PAD);
+    if (s_rowbase[nrows] <= (uint32_t)cap) {
+        float *px = reinterpret_cast<float *>(rp_dyn), *py = px + (cap + RP_PAD), *pz = py + (cap + RP_PAD);
         for (int r = 0; r < nrows; ++r) {
             const RowInfo &ri = bk.row[r];
             const uint32_t rb = s_rowbase[r];
@@ -133,11 +151,14 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
         __syncthreads();
         // Work items = (chunk of 32 queries, part of the rows), part-major; warp w starts with item w and
         // claims the next unclaimed one when it is done.  A home cell of ~82 queries is three chunks: with
-        // one static chunk per warp the fourth warp of the CTA had nothing to do and the 51 kB of the CTA
-        // stayed allocated until the slowest warp was through all 14 rows.
+        // two row parts that is one item for each of the six warps.
         const int nchunk = (int)((qs1 - qs0 + 31u) >> 5);
-        const int nparts = nrows >= 4 ? 2 : 1;
+        const int nparts = nrows >= 4 ? max(2, (nrows + RP_PARTROWS - 1) / RP_PARTROWS) : 1;
         const int nitems = nchunk * nparts;
+        const uint32_t lq0 = smem_u32(s_queue) + (uint32_t)(warp * RP_LQ * 64 + lane * 2);
+        const uint32_t px32 = smem_u32(px);
+        const uint32_t PLANE = (uint32_t)(cap + RP_PAD) * 4u;         // bytes between the planes
+        const uint32_t wq0 = smem_u32(s_queue) + (uint32_t)(NW * RP_LQ * 64 + warp * RP_WQ * 4);
         for (int item = warp; item < nitems;) {
             const int part = item / nchunk, chunk = item - part * nchunk;
             const int ra = nrows * part / nparts, rb = nrows * (part + 1) / nparts;
@@ -155,33 +176,72 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
             }
             const int cmin = (int)__reduce_min_sync(0xffffffffu, active ? (unsigned)cxl : 0x7fffffffu);
             const int cmax = (int)__reduce_max_sync(0xffffffffu, active ? (unsigned)cxl : 0u);
-            // float64 evaluation of up to 64 queued survivors, two per lane: the queue names the lane
-            // that owns the query (a shuffle instead of a gather), both candidates are fetched before
-            // either is used, and the accepted pairs of both rounds share one atomic
-            auto drain = [&](uint32_t first, uint32_t count) {
+            uint32_t lqp = lq0;                                     // where this lane's next survivor goes (64 bytes per entry)
+            const uint32_t lqlim = lq0 + (uint32_t)(RP_LQ - 4) * 64u;
+            uint32_t nwq = 0;                                       // entries in the compacted warp queue (warp-uniform)
+            // float64 evaluation of 64 (or the last < 64) entries of the warp queue, two per lane: an entry
+            // is (tile position | row within the part << 12 | owner lane << 16); the query comes by
+            // shuffle from its lane, the run -- and with it the global slot and the image -- from the
+            // row's descriptor; both candidate gathers are in flight together and the accepted pairs of
+            // both rounds share one atomic.
+            auto evaluate64 = [&](uint32_t first, uint32_t count) {
                 __syncwarp();
                 const bool v0 = (uint32_t)lane < count, v1 = (uint32_t)lane + 32u < count;
-                const uint32_t e0 = first + lane, e1 = e0 + 32u;
-                const uint32_t l0 = v0 ? qq[e0] : 0u, l1 = v1 ? qq[e1] : 0u;
-                const int code0 = v0 ? qi[e0] : 0, code1 = v1 ? qi[e1] : 0;
+                uint32_t e0 = 0, e1 = 0;
+                if (v0) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e0) : "r"(wq0 + 4u * (first + lane)));
+                if (v1) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e1) : "r"(wq0 + 4u * (first + lane + 32u)));
+                auto locate = [&](uint32_t e, int &ia, int &ib, int &ic) -> uint32_t {
+                    const int r = ra + (int)((e >> 12) & 15u);
+                    const RowInfo &ri = bk.row[r];
+                    const uint32_t t = (e & 4095u) - s_rowbase[r];
+                    const int sx = t >= ri.end[1] ? 2 : (t >= ri.end[0] ? 1 : 0);
+                    ia = 1 - sx; ib = -ri.ib; ic = -ri.ic;
+                    return ri.g[sx] + (t - (sx ? ri.end[sx - 1] : 0u));
+                };
+                int a0 = 0, b0 = 0, g0 = 0, a1 = 0, b1 = 0, g1 = 0;
+                const uint32_t s0 = locate(e0, a0, b0, g0), s1 = locate(e1, a1, b1, g1);
                 float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-                if (v0) c0 = c_atoms[qc[e0]];
-                if (v1) c1 = c_atoms[qc[e1]];
+                if (v0) c0 = c_atoms[s0];
+                if (v1) c1 = c_atoms[s1];
+                const uint32_t l0 = e0 >> 16, l1 = e1 >> 16;
                 float4 q0, q1;
                 q0.x = __shfl_sync(0xffffffffu, q.x, l0); q0.y = __shfl_sync(0xffffffffu, q.y, l0);
                 q0.z = __shfl_sync(0xffffffffu, q.z, l0); q0.w = __shfl_sync(0xffffffffu, q.w, l0);
                 q1.x = __shfl_sync(0xffffffffu, q.x, l1); q1.y = __shfl_sync(0xffffffffu, q.y, l1);
                 q1.z = __shfl_sync(0xffffffffu, q.z, l1); q1.w = __shfl_sync(0xffffffffu, q.w, l1);
-                auto exact = [&](const float4 &qa, const float4 &ca, int code) {
+                auto exact = [&](const float4 &qa, const float4 &ca, int ia, int ib, int ic) {
                     if (MIC == MIC_TRICLINIC) {
                         D3 d = sep_f32(qa.x, qa.y, qa.z, ca.x, ca.y, ca.z), img;
-                        return tric_image_d2(d, box.h, (code & 3) - 1, -(((code >> 2) & 3) - 1), -(((code >> 4) & 3) - 1), img);
+                        return tric_image_d2(d, box.h, ia, ib, ic, img);
                     }
                     return pair_d2_exact<MIC>(qa.x, qa.y, qa.z, ca.x, ca.y, ca.z, box);
                 };
-                const double d0 = exact(q0, c0, code0), d1 = exact(q1, c1, code1);
+                const double d0 = exact(q0, c0, a0, b0, g0), d1 = exact(q1, c1, a1, b1, g1);
                 sink.hit2(v0 && d0 <= sp.d2_max && d0 > sp.d2_min, __float_as_int(q0.w), __float_as_int(c0.w), d0,
                           v1 && d1 <= sp.d2_max && d1 > sp.d2_min, __float_as_int(q1.w), __float_as_int(c1.w), d1);
+                __syncwarp();
+            };
+            // bulk compaction of the 32 per-lane queues into the warp queue: one ballot per slot row
+            auto drain = [&]() {
+                __syncwarp();
+                const uint32_t cnt = (lqp - lq0) >> 6;
+                const uint32_t rows = __reduce_max_sync(0xffffffffu, cnt);
+                const uint32_t tag = (uint32_t)lane << 16, lt = (1u << lane) - 1u;
+                for (uint32_t j = 0; j < rows; ++j) {
+                    const bool v = j < cnt;
+                    const uint32_t m = __ballot_sync(0xffffffffu, v);
+                    if (v) {
+                        uint32_t e;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(lq0 + 64u * j));
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(wq0 + 4u * (nwq + __popc(m & lt))), "r"(e | tag) : "memory");
+                    }
+                    nwq += __popc(m);
+                    if (nwq >= 64u) {
+                        evaluate64(nwq - 64u, 64u);
+                        nwq -= 64u;
+                    }
+                }
+                lqp = lq0;
                 __syncwarp();
             };
             for (int r = ra; r < rb; ++r) {
@@ -200,7 +260,8 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                 const float qrx = q.x - ((float)ri.ib * hy[0] + (float)ri.ic * hz[0]);
                 const float qry = q.y - ((float)ri.ib * hy[1] + (float)ri.ic * hz[1]);
                 const float qrz = q.z - ((float)ri.ib * hy[2] + (float)ri.ic * hz[2]);
-                const uint32_t rb = s_rowbase[r];
+                const uint32_t rbase = s_rowbase[r];
+                const uint32_t rtag = (uint32_t)(r - ra) << 12;
                 uint32_t sb = 0;
 #pragma unroll 1
                 for (int s = 0; s < 3; ++s) {
@@ -208,58 +269,41 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                     const uint32_t a = max(wlo, sb), e = min(whi, se);      // warp-uniform
                     if (a < e) {
                         const float sgn = (float)(1 - s);
-                        const float qx = qrx + sgn * hx[0], qy = qry + sgn * hx[1], qz = qrz + sgn * hx[2];
-                        const uint32_t code = (uint32_t)((1 - s) + 1) | (uint32_t)(ri.ib + 1) << 2 | (uint32_t)(ri.ic + 1) << 4;
-                        const uint32_t gbase = ri.g[s] - sb;
+                        // minus the translated query, twice: dx = c + (-q) has the same square as q - c
+                        const float nx = -(qrx + sgn * hx[0]), ny = -(qry + sgn * hx[1]), nz = -(qrz + sgn * hx[2]);
+                        const float2 nqx = make_float2(nx, nx), nqy = make_float2(ny, ny), nqz = make_float2(nz, nz);
                         // the lane's own part of this run as (first, width) for one unsigned compare
                         const uint32_t lo2 = max(lo, a), hi2 = min(hi, e);
                         const uint32_t width = hi2 > lo2 ? hi2 - lo2 : 0u;
-                        for (uint32_t qd = (rb + a) & ~3u; qd < rb + e; qd += 4u * RP_NQ) {
-                            float cxs[4 * RP_NQ], cys[4 * RP_NQ], czs[4 * RP_NQ];
+                        const uint32_t qd0 = (rbase + a) & ~3u, qd1 = rbase + e;
+                        uint32_t rel = qd0 - rbase - lo2;                   // row coordinate of candidate 0, minus lo2 (mod 2^32)
+                        uint32_t val = qd0 | rtag;
+                        for (uint32_t ptr = px32 + 4u * qd0; ptr < px32 + 4u * qd1; ptr += 16u, rel += 4u, val += 4u) {
+                            float4 X, Y, Z;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(X.x), "=f"(X.y), "=f"(X.z), "=f"(X.w) : "r"(ptr));
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Y.x), "=f"(Y.y), "=f"(Y.z), "=f"(Y.w) : "r"(ptr + PLANE));
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Z.x), "=f"(Z.y), "=f"(Z.z), "=f"(Z.w) : "r"(ptr + 2u * PLANE));
+                            const float2 dxa = __fadd2_rn(make_float2(X.x, X.y), nqx), dxb = __fadd2_rn(make_float2(X.z, X.w), nqx);
+                            const float2 dya = __fadd2_rn(make_float2(Y.x, Y.y), nqy), dyb = __fadd2_rn(make_float2(Y.z, Y.w), nqy);
+                            const float2 dza = __fadd2_rn(make_float2(Z.x, Z.y), nqz), dzb = __fadd2_rn(make_float2(Z.z, Z.w), nqz);
+                            const float2 da = __ffma2_rn(dxa, dxa, __ffma2_rn(dya, dya, __fmul2_rn(dza, dza)));
+                            const float2 db = __ffma2_rn(dxb, dxb, __ffma2_rn(dyb, dyb, __fmul2_rn(dzb, dzb)));
+                            const float d2f[4] = { da.x, da.y, db.x, db.y };
 #pragma unroll
-                            for (int g = 0; g < RP_NQ; ++g) {
-                                const float4 X = *reinterpret_cast<const float4 *>(px + qd + 4 * g);
-                                const float4 Y = *reinterpret_cast<const float4 *>(py + qd + 4 * g);
-                                const float4 Z = *reinterpret_cast<const float4 *>(pz + qd + 4 * g);
-                                cxs[4 * g] = X.x; cxs[4 * g + 1] = X.y; cxs[4 * g + 2] = X.z; cxs[4 * g + 3] = X.w;
-                                cys[4 * g] = Y.x; cys[4 * g + 1] = Y.y; cys[4 * g + 2] = Y.z; cys[4 * g + 3] = Y.w;
-                                czs[4 * g] = Z.x; czs[4 * g + 1] = Z.y; czs[4 * g + 2] = Z.z; czs[4 * g + 3] = Z.w;
-                            }
-                            const uint32_t rel = qd - rb - lo2;     // row coordinate of candidate 0, minus lo2 (mod 2^32)
-                            uint32_t m[4 * RP_NQ], many = 0u;
-                            bool keep[4 * RP_NQ];
-#pragma unroll
-                            for (int k = 0; k < 4 * RP_NQ; ++k) {
-                                const float tx = qx - cxs[k], ty = qy - cys[k], tz = qz - czs[k];
-                                const float d2f = fmaf(tx, tx, fmaf(ty, ty, tz * tz));
-                                keep[k] = d2f <= sp.d2_filter && rel + (uint32_t)k < width;
-                                m[k] = __ballot_sync(0xffffffffu, keep[k]);
-                                many |= m[k];
-                            }
-                            if (many) {
-#pragma unroll
-                                for (int k = 0; k < 4 * RP_NQ; ++k) {
-                                    if (m[k] == 0u) continue;
-                                    if (keep[k]) {
-                                        const uint32_t at = nqueued + __popc(m[k] & ((1u << lane) - 1u));
-                                        qq[at] = (uint32_t)lane;
-                                        qc[at] = gbase + (qd - rb) + (uint32_t)k;
-                                        qi[at] = (uint8_t)code;
-                                    }
-                                    nqueued += __popc(m[k]);
-                                    if (nqueued >= 64u) {
-                                        drain(nqueued - 64u, 64u);
-                                        nqueued -= 64u;
-                                    }
+                            for (int k = 0; k < 4; ++k) {
+                                if (d2f[k] <= sp.d2_filter && rel + (uint32_t)k < width) {
+                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(lqp), "r"(val + (uint32_t)k) : "memory");
+                                    lqp += 64u;
                                 }
                             }
+                            if (__any_sync(0xffffffffu, lqp > lqlim)) drain();
                         }
                     }
                     sb = se;
                 }
             }
-            if (nqueued) drain(0u, nqueued);                         // < 64 left
-            nqueued = 0u;
+            if (__any_sync(0xffffffffu, lqp != lq0)) drain();
+            if (nwq) evaluate64(0u, nwq);                             // < 64 left
             uint32_t nxt = 0;
             if (lane == 0) nxt = atomicAdd(&s_next, 1u);
             item = (int)__shfl_sync(0xffffffffu, nxt, 0);
@@ -309,13 +353,13 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                     hi = bk.off[r][min(cxl + span + 1, ncell)];
                     if (home) lo += (qslot - bk.qst[cxl]) + 1;     // later atoms of the own cell
                 }
-                const uint32_t pe = min(p + (uint32_t)RP_TILE, ri.end[2]);
+                const uint32_t pe = min(p + rtile, ri.end[2]);
                 const uint32_t wlo = max(bk.off[r][cmin], p), whi = min(bk.off[r][min(cmax + span + 1, ncell)], pe);
                 // the row's lattice translation goes onto the query: q - (c + t) = (q - t) - c
                 const float qrx = q.x - ((float)ri.ib * hy[0] + (float)ri.ic * hz[0]);
                 const float qry = q.y - ((float)ri.ib * hy[1] + (float)ri.ic * hz[1]);
                 const float qrz = q.z - ((float)ri.ib * hy[2] + (float)ri.ic * hz[2]);
-                const float4 *tb = tile[b];
+                const float4 *tb = tile0 + (uint32_t)b * rtile;
                 uint32_t sb = 0;
 #pragma unroll 1
                 for (int s = 0; s < 3; ++s) {
