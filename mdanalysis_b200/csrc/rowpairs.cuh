@@ -37,9 +37,19 @@ namespace mdagpu {
 constexpr int RP_TILE = 1024;             // staged candidates per buffer (row-by-row path)
 constexpr int RP_ALL = 3584;              // staged candidates of ALL rows (plane path): 3 x 14 kB
 constexpr int RP_QUEUE = 96;              // queued survivors per warp (drained at >= 32)
-constexpr int RP_PAD = 4;                 // sentinels behind the last row (a trip may read past the end)
-constexpr int RP_THREADS = 192;           // 6 warps: the 3 chunks x 2 row parts of a ~80-query home cell, one item each
-constexpr int RP_LQ = 24;                 // survivors a lane can hold between two drains
+constexpr int RP_PAD = 8;                 // sentinels behind the last row (a trip may read past the end)
+#ifndef RP_THREADS_
+#define RP_THREADS_ 128
+#endif
+#ifndef RP_LQ_
+#define RP_LQ_ 24
+#endif
+#ifndef RP_MINB_
+#define RP_MINB_ 6
+#endif
+constexpr int RP_THREADS = RP_THREADS_;   // 4 warps claim the (chunk, row part) items of the CTA; 6 CTAs of 80 registers per SM
+                                          // (profiles/microbench/fastns_variants_b200.txt: 192 / 160 / 256 threads are within 5 %)
+constexpr int RP_LQ = RP_LQ_;                 // survivors a lane can hold between two drains
 constexpr int RP_WQ = 128;                // compacted warp queue (evaluated 64 at a time)
 constexpr int RP_PARTROWS = 16;           // rows per work item (4 bits of a queue entry)
 // dynamic shared memory for a plane capacity of `cap` candidates (a multiple of 4, <= RP_ALL); the two
@@ -48,7 +58,7 @@ __host__ __device__ constexpr size_t rp_dyn_bytes(int cap) { return 3 * (size_t)
 constexpr int RP_MINCAP = 512;
 
 template <int MIC, bool SELF, class Sink, int T_ = RP_THREADS>
-__global__ void __launch_bounds__(T_)
+__global__ void __launch_bounds__(T_, RP_MINB_)
 row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
                  const float4 *__restrict__ c_atoms, const uint32_t *__restrict__ c_start,
                  const FrameGeom *__restrict__ fgs, int per_frame, RowParams rp, SearchParams sp, Sink sink, int cap)
@@ -177,7 +187,7 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
             const int cmin = (int)__reduce_min_sync(0xffffffffu, active ? (unsigned)cxl : 0x7fffffffu);
             const int cmax = (int)__reduce_max_sync(0xffffffffu, active ? (unsigned)cxl : 0u);
             uint32_t lqp = lq0;                                     // where this lane's next survivor goes (64 bytes per entry)
-            const uint32_t lqlim = lq0 + (uint32_t)(RP_LQ - 4) * 64u;
+            const uint32_t lqlim = lq0 + (uint32_t)(RP_LQ - 8) * 64u;
             uint32_t nwq = 0;                                       // entries in the compacted warp queue (warp-uniform)
             // float64 evaluation of 64 (or the last < 64) entries of the warp queue, two per lane: an entry
             // is (tile position | row within the part << 12 | owner lane << 16); the query comes by
@@ -278,7 +288,8 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                         const uint32_t qd0 = (rbase + a) & ~3u, qd1 = rbase + e;
                         uint32_t rel = qd0 - rbase - lo2;                   // row coordinate of candidate 0, minus lo2 (mod 2^32)
                         uint32_t val = qd0 | rtag;
-                        for (uint32_t ptr = px32 + 4u * qd0; ptr < px32 + 4u * qd1; ptr += 16u, rel += 4u, val += 4u) {
+                        // four candidates: three LDS.128, packed distance, a predicated 2-byte store per survivor
+                        auto trip = [&](uint32_t ptr, uint32_t rel4, uint32_t val4) {
                             float4 X, Y, Z;
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(X.x), "=f"(X.y), "=f"(X.z), "=f"(X.w) : "r"(ptr));
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Y.x), "=f"(Y.y), "=f"(Y.z), "=f"(Y.w) : "r"(ptr + PLANE));
@@ -291,11 +302,17 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                             const float d2f[4] = { da.x, da.y, db.x, db.y };
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (d2f[k] <= sp.d2_filter && rel + (uint32_t)k < width) {
-                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(lqp), "r"(val + (uint32_t)k) : "memory");
+                                if (d2f[k] <= sp.d2_filter && rel4 + (uint32_t)k < width) {
+                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(lqp), "r"(val4 + (uint32_t)k) : "memory");
                                     lqp += 64u;
                                 }
                             }
+                        };
+                        // two trips per queue check (a trip past the end of the run reads the next row or the
+                        // sentinels: outside every lane's window)
+                        for (uint32_t ptr = px32 + 4u * qd0; ptr < px32 + 4u * qd1; ptr += 32u, rel += 8u, val += 8u) {
+                            trip(ptr, rel, val);
+                            trip(ptr + 16u, rel + 4u, val + 4u);
                             if (__any_sync(0xffffffffu, lqp > lqlim)) drain();
                         }
                     }
