@@ -47,12 +47,42 @@ def sqrt_le_threshold(e):
     return x
 
 
+_THRESHOLD_CACHE = {}
+
+
 def histogram_thresholds(edges):
-    """d2 thresholds equivalent to binning sqrt(d2) with np.histogram on ``edges``."""
-    t = np.empty(len(edges), dtype=np.float64)
-    for k, e in enumerate(edges[:-1]):
-        t[k] = sqrt_ge_threshold(e)
-    t[-1] = sqrt_le_threshold(edges[-1])
+    """d2 thresholds equivalent to binning sqrt(d2) with np.histogram on ``edges``.
+
+    Vectorised (the per-edge scalar search cost 1.3 ms per ``run()`` for 150 bins -- as much as
+    the rest of the host side of a run) and cached per edge array: ``t[k]`` = smallest float64
+    ``x`` with ``sqrt(x) >= edges[k]`` (``sqrt_ge_threshold``), ``t[-1]`` = largest ``x`` with
+    ``sqrt(x) <= edges[-1]`` (``sqrt_le_threshold``).
+    """
+    e = np.ascontiguousarray(edges, dtype=np.float64)
+    key = e.tobytes()
+    hit = _THRESHOLD_CACHE.get(key)
+    if hit is not None:
+        return hit.copy()
+    x = e * e
+    # walk to the boundary: first down while the predecessor still satisfies sqrt >= e, then up
+    # while x itself does not (a handful of steps: e * e is within an ulp or two of the boundary)
+    for _ in range(64):
+        prev = np.nextafter(x, -np.inf)
+        with np.errstate(invalid="ignore"):
+            move = (np.sqrt(prev) >= e) & (x > 0.0)
+        if not move.any():
+            break
+        x = np.where(move, prev, x)
+    for _ in range(64):
+        move = np.sqrt(x) < e
+        if not move.any():
+            break
+        x = np.where(move, np.nextafter(x, np.inf), x)
+    t = np.where(e <= 0.0, 0.0, x)                        # sqrt_ge_threshold: edges <= 0 -> 0
+    t[-1] = sqrt_le_threshold(e[-1])
+    if len(_THRESHOLD_CACHE) > 64:
+        _THRESHOLD_CACHE.clear()
+    _THRESHOLD_CACHE[key] = t.copy()
     return t
 
 
@@ -170,9 +200,11 @@ class InterRDF(BlockAnalysis):
             counts = np.zeros(nbins, dtype=np.uint64)
         rc2 = float(self._maxrange) * float(self._maxrange)           # nsgrid.pyx:540
         d2_brute = float(sqrt_le_threshold(self._maxrange))           # d <= max_cutoff
-        for mode in sorted(set(modes)):
+        kinds = sorted(set(modes))
+        for mode in kinds:
             use_grid, mic, wrap = mode
-            fidx = np.flatnonzero([m == mode for m in modes])
+            # (one mode for every frame -- a constant cell -- needs no per-frame comparison)
+            fidx = np.arange(blk.n_frames) if len(kinds) == 1 else np.flatnonzero([m == mode for m in modes])
             whole = len(fidx) == blk.n_frames
             A = blk.positions if whole else blk.positions[fidx if not dev else torch.as_tensor(fidx, device=blk.positions.device)]
             B = None if self._same else (b2.positions if whole else b2.positions[fidx if not dev else torch.as_tensor(fidx, device=blk.positions.device)])
