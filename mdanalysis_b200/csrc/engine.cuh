@@ -52,18 +52,18 @@ struct FrameGeom {
 __global__ void cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
                                 const FrameGeom *__restrict__ fg, int per_frame, int wrap,
                                 uint32_t *__restrict__ keys, uint32_t *__restrict__ counts,
-                                unsigned *__restrict__ flag);
+                                uint32_t *__restrict__ ranks, unsigned *__restrict__ flag);
 // exclusive scan of the per-cell counts into starts[], one CTA per frame (frame f starts at
 // f * n_atoms); starts[total_cells] = total
 __global__ void exclusive_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ starts,
                                       const FrameGeom *__restrict__ fgs, int per_frame, uint64_t n_atoms,
                                       uint64_t nframes);
-// sorted[starts[key] + slot] = {x,y,z,i}; cursor must be zeroed; wraps like cell_key_kernel
+// sorted[starts[key] + ranks[t]] = {x,y,z,i} (ranks: the key kernel's atomicAdd results); wraps like cell_key_kernel
 __global__ void cell_scatter_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
                                     const FrameGeom *__restrict__ fg, int per_frame, int wrap,
                                     const uint32_t *__restrict__ keys,
                                     const uint32_t *__restrict__ starts,
-                                    uint32_t *__restrict__ cursor, float4 *__restrict__ sorted,
+                                    const uint32_t *__restrict__ ranks, float4 *__restrict__ sorted,
                                     uint32_t *__restrict__ sorted_key);
 
 struct CellList {
@@ -78,7 +78,8 @@ struct CellList {
 
 // Builds the sorted cell list of `xyz` [nframes, n, 3] (device pointer).
 int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameGeom *fg_dev,
-                    int per_frame, uint64_t total_cells, int wrap, cudaStream_t st, CellList *out);
+                    int per_frame, uint64_t total_cells, int wrap, cudaStream_t st, CellList *out,
+                    bool want_sorted_key = true);
 
 // ---- FP32 pre-filter ----------------------------------------------------------------
 // Returns an FP32 estimate of the minimum-image d2 whose relative error is far

@@ -85,15 +85,17 @@ void grid_geometry_single(GridGeom *g)
 __global__ void __launch_bounds__(256)
 cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
                 const FrameGeom *__restrict__ fgs, int per_frame, int wrap,
-                uint32_t *__restrict__ keys, uint32_t *__restrict__ counts, unsigned *__restrict__ flag)
+                uint32_t *__restrict__ keys, uint32_t *__restrict__ counts, uint32_t *__restrict__ ranks,
+                unsigned *__restrict__ flag)
 {
-    const uint64_t total = n * nframes;
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // (n * nframes < 2^32, checked by build_cell_list: 32-bit index arithmetic, no 64-bit division)
+    const uint32_t total = (uint32_t)(n * nframes), n32 = (uint32_t)n;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; t < total; t += stride) {
-        const uint64_t f = t / n;
+    for (uint64_t t64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t64 < total; t64 += stride) {
+        const uint32_t t = (uint32_t)t64;
+        const uint32_t f = t / n32;
         const FrameGeom &fg = fgs[per_frame ? f : 0];
-        float x = xyz[3 * t], y = xyz[3 * t + 1], z = xyz[3 * t + 2];
+        float x = xyz[3 * (uint64_t)t], y = xyz[3 * (uint64_t)t + 1], z = xyz[3 * (uint64_t)t + 2];
         if (wrap) wrap_any(x, y, z, fg.box);
         int64_t cell = 0;
         if (fg.grid.ncell_total > 1) {
@@ -107,7 +109,8 @@ cell_key_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
         const int64_t base = per_frame ? fg.cell_base : (int64_t)f * fg.grid.ncell_total;
         const uint32_t key = (uint32_t)(base + cell);
         keys[t] = key;
-        atomicAdd(&counts[key], 1u);
+        // the count before this atom is its rank in the cell: the scatter needs no second atomic
+        ranks[t] = atomicAdd(&counts[key], 1u);
     }
 }
 
@@ -164,26 +167,26 @@ __global__ void __launch_bounds__(256)
 cell_scatter_kernel(const float *__restrict__ xyz, uint64_t n, uint64_t nframes,
                     const FrameGeom *__restrict__ fgs, int per_frame, int wrap,
                     const uint32_t *__restrict__ keys, const uint32_t *__restrict__ starts,
-                    uint32_t *__restrict__ cursor, float4 *__restrict__ sorted,
+                    const uint32_t *__restrict__ ranks, float4 *__restrict__ sorted,
                     uint32_t *__restrict__ sorted_key)
 {
-    const uint64_t total = n * nframes;
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = (uint32_t)(n * nframes), n32 = (uint32_t)n;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; t < total; t += stride) {
-        const uint64_t f = t / n;
+    for (uint64_t t64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t64 < total; t64 += stride) {
+        const uint32_t t = (uint32_t)t64;
+        const uint32_t f = t / n32;
         const FrameGeom &fg = fgs[per_frame ? f : 0];
-        float x = xyz[3 * t], y = xyz[3 * t + 1], z = xyz[3 * t + 2];
+        float x = xyz[3 * (uint64_t)t], y = xyz[3 * (uint64_t)t + 1], z = xyz[3 * (uint64_t)t + 2];
         if (wrap == 1) wrap_any(x, y, z, fg.box);   // wrap == 2: binned wrapped, stored as given
         const uint32_t key = keys[t];
-        const uint32_t slot = starts[key] + atomicAdd(&cursor[key], 1u);
-        sorted[slot] = make_float4(x, y, z, __int_as_float((int)(t - f * n)));
-        sorted_key[slot] = key;
+        const uint32_t slot = starts[key] + ranks[t];
+        sorted[slot] = make_float4(x, y, z, __int_as_float((int)(t - f * n32)));
+        if (sorted_key) sorted_key[slot] = key;     // only the thread-per-query kernels read it
     }
 }
 
 int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameGeom *fg_dev,
-                    int per_frame, uint64_t total_cells, int wrap, cudaStream_t st, CellList *cl)
+                    int per_frame, uint64_t total_cells, int wrap, cudaStream_t st, CellList *cl, bool want_sorted_key)
 {
     const uint64_t total = n * nframes;
     MDA_REQUIRE(total < 0xffffffffull && total_cells < 0xfffffff0ull,
@@ -193,13 +196,12 @@ int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameG
     MDA_CUDA(cl->keys.alloc(total * sizeof(uint32_t), st));
     MDA_CUDA(cl->counts.alloc(total_cells * sizeof(uint32_t), st));
     MDA_CUDA(cl->starts.alloc((total_cells + 1) * sizeof(uint32_t), st));
-    MDA_CUDA(cl->cursor.alloc(total_cells * sizeof(uint32_t), st));
+    MDA_CUDA(cl->cursor.alloc((total ? total : 1) * sizeof(uint32_t), st));       // rank of every atom in its cell
     MDA_CUDA(cl->sorted.alloc(total * sizeof(float4), st));
-    MDA_CUDA(cl->sorted_key.alloc(total * sizeof(uint32_t), st));
+    if (want_sorted_key) MDA_CUDA(cl->sorted_key.alloc(total * sizeof(uint32_t), st));
     MDA_CUDA(cl->flag.alloc(sizeof(unsigned), st));
     MDA_CUDA(cudaMemsetAsync(cl->flag.p, 0, sizeof(unsigned), st));
     MDA_CUDA(cudaMemsetAsync(cl->counts.p, 0, total_cells * sizeof(uint32_t), st));
-    MDA_CUDA(cudaMemsetAsync(cl->cursor.p, 0, total_cells * sizeof(uint32_t), st));
     if (total == 0) {
         MDA_CUDA(cudaMemsetAsync(cl->starts.p, 0, (total_cells + 1) * sizeof(uint32_t), st));
         return MDAGPU_OK;
@@ -208,14 +210,14 @@ int build_cell_list(const float *xyz, uint64_t n, uint64_t nframes, const FrameG
     const unsigned cap = (unsigned)num_sms() * 16;
     if (grid > cap) grid = cap;
     MDA_LAUNCH(cell_key_kernel, grid, 256, 0, st, xyz, n, nframes, fg_dev, per_frame, wrap,
-               cl->keys.as<uint32_t>(), cl->counts.as<uint32_t>(), cl->flag.as<unsigned>());
+               cl->keys.as<uint32_t>(), cl->counts.as<uint32_t>(), cl->cursor.as<uint32_t>(), cl->flag.as<unsigned>());
     MDA_CHECK_LAUNCH();
     MDA_LAUNCH(exclusive_scan_kernel, (unsigned)nframes, 1024, 0, st, cl->counts.as<uint32_t>(),
                cl->starts.as<uint32_t>(), fg_dev, per_frame, n, nframes);
     MDA_CHECK_LAUNCH();
     MDA_LAUNCH(cell_scatter_kernel, grid, 256, 0, st, xyz, n, nframes, fg_dev, per_frame, wrap,
                cl->keys.as<uint32_t>(), cl->starts.as<uint32_t>(), cl->cursor.as<uint32_t>(),
-               cl->sorted.as<float4>(), cl->sorted_key.as<uint32_t>());
+               cl->sorted.as<float4>(), want_sorted_key ? cl->sorted_key.as<uint32_t>() : nullptr);
     MDA_CHECK_LAUNCH();
     return MDAGPU_OK;
 }

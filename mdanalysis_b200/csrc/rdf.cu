@@ -810,11 +810,12 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
         }
         const FrameGeom *fgd = fg_dev.as<FrameGeom>();
         CellList cl, ql;
-        int rc = build_cell_list(same ? a_dev : b_dev, nb, fc, fgd, boxes_per_frame, total_cells, wrap, st, &cl);
+        // (none of the RDF traversals reads the cell key of a sorted atom: one scattered store less per atom)
+        int rc = build_cell_list(same ? a_dev : b_dev, nb, fc, fgd, boxes_per_frame, total_cells, wrap, st, &cl, false);
         if (rc) return rc;
         if (!same) {
             rc = build_cell_list(a_dev, na, fc, fgd, boxes_per_frame,
-                                 total_cells, wrap, st, &ql);
+                                 total_cells, wrap, st, &ql, false);
             if (rc) return rc;
         }
         const CellList &qq = same ? cl : ql;
