@@ -38,6 +38,29 @@ def test_fastns_search_and_self_search(oracle, bname, cutoff, n):
     assert r.get_pairs().dtype == np.intp and r.get_pair_distances().dtype == np.float64
 
 
+@pytest.mark.parametrize("bname", ["ortho", "tric60"])
+def test_fastns_clustered_density(oracle, bname):
+    """Strongly non-uniform density: the row kernel sizes its tile from the MEAN cell occupancy
+    (csrc/nsgrid.cu choose_traversal), so the cells of a dense blob do not fit and take the
+    row-by-row staging with its run-time buffer size (csrc/rowpairs.cuh); sparse cells next to
+    them take the plane path.  Same pair sets and distances as the oracle either way."""
+    from mdanalysis_b200.lib.nsgrid import FastNS
+    rng = np.random.default_rng(77)
+    box = BOXES[bname]
+    tv = oracle.triclinic_vectors(box).astype(np.float64)
+    centre = np.array([0.5, 0.5, 0.5]) @ tv
+    xyz = np.concatenate([(rng.random((6000, 3)) @ tv), centre + rng.normal(0.0, 3.0, (2500, 3)),
+                          (np.array([0.02, 0.97, 0.5]) @ tv) + rng.normal(0.0, 1.5, (600, 3))]).astype(np.float32)
+    q = np.concatenate([(rng.random((500, 3)) @ tv), centre + rng.normal(0.0, 4.0, (300, 3))]).astype(np.float32)
+    cutoff = 4.0
+    g, o = FastNS(cutoff, xyz, box), oracle.FastNS(cutoff, xyz, box)
+    r, ro = g.self_search(), o.self_search()
+    k = same_pairs((r.get_pairs(), r.get_pair_distances()), (ro.get_pairs(), ro.get_pair_distances()), True)
+    assert k > 500_000                                               # the blobs dominate
+    r, ro = g.search(q), o.search(q)
+    same_pairs((r.get_pairs(), r.get_pair_distances()), (ro.get_pairs(), ro.get_pair_distances()))
+
+
 def test_fastns_errors_and_edges(oracle):
     from mdanalysis_b200.lib.nsgrid import FastNS
     xyz = np.random.default_rng(0).random((100, 3)).astype(np.float32) * 10
