@@ -49,6 +49,56 @@ void grid_geometry_ortho_free(double cutoff, const float *L3, const double *orig
     g->ncell_total = total;
 }
 
+// ---- triclinic cells: is a (2W + 1)^3 stencil on grid `g` COMPLETE for this cutoff? ----
+// cell_of() (geom.cuh, the reference's coord2cellxyz, nsgrid.pyx:435-446) maps a position to the
+// cell coordinates  z' = z / cs_zz,  y' = (y - t_yz z) / cs_yy,  x' = (x - t_xy y - t_xz z) / cs_xx
+// with the tilt ratios t_xy = b_x / b_y, t_xz = c_x / c_z, t_yz = c_y / c_z.  Two positions within the
+// cutoff differ by at most  r_c / cs_zz,  r_c sqrt(1 + t_yz^2) / cs_yy,  r_c sqrt(1 + t_xy^2 + t_xz^2) / cs_xx
+// (the maximum of a linear form over a sphere).  A shift by the lattice vectors a, b changes the cell
+// coordinates by whole grids; a shift by c moves x' by -(b_x c_y / b_y) / cs_xx as well (the reference
+// shears x by t_xy y, not by the fractional coordinate): a pair across the periodic z boundary is that
+// much further apart in x'.  The stencil is complete when W cells cover these reaches.  This is what
+// decides whether the reference's own search (W = 1 on its grid) returns EVERY pair within the
+// cutoff (for [40, 35, 50, 70, 80, 100] it does not) -- only then may a finer
+// grid be used for a triclinic InterRDF.
+static bool tric_stencil_complete(const GridGeom &g, const float *h9, double cutoff, int W)
+{
+    const double rc = cutoff * (1.0 + 1e-4) + 1e-4;
+    const double fx = sqrt(1.0 + g.cs[3] * g.cs[3] + g.cs[6] * g.cs[6]), fy = sqrt(1.0 + g.cs[7] * g.cs[7]);
+    const double dx = fabs((double)h9[3] * (double)h9[7] / (double)h9[4]);
+    return (double)W * g.cs[0] >= rc * fx + dx && (double)W * g.cs[4] >= rc * fy && (double)W * g.cs[8] >= rc;
+}
+
+// Triclinic grid of the library's own: the reference's cell coordinates (same tilt ratios, so
+// cell_of() applies unchanged) with cells just wide enough for a complete (2W + 1)^3 stencil.
+static void grid_geometry_triclinic_free(double cutoff, int W, const float *h9, GridGeom *g)
+{
+    g->triclinic = 1;
+    g->pbc = 1;
+    for (int k = 0; k < 9; ++k) g->cs[k] = 0.0;
+    g->origin[0] = g->origin[1] = g->origin[2] = 0.0;
+    g->cs[3] = (double)(h9[3] / h9[4]);
+    g->cs[6] = (double)(h9[6] / h9[8]);
+    g->cs[7] = (double)(h9[7] / h9[8]);
+    const double rc = cutoff * (1.0 + 2e-4) + 1e-3;
+    const double fx = sqrt(1.0 + g->cs[3] * g->cs[3] + g->cs[6] * g->cs[6]), fy = sqrt(1.0 + g->cs[7] * g->cs[7]);
+    const double dx = fabs((double)h9[3] * (double)h9[7] / (double)h9[4]);
+    const double need[3] = { (rc * fx + dx) / W, rc * fy / W, rc / W };
+    const double edge[3] = { (double)h9[0], (double)h9[4], (double)h9[8] };
+    int64_t total = 1;
+    for (int k = 0; k < 3; ++k) {
+        double nc = floor(edge[k] / need[k]);
+        if (!(nc >= 1.0)) nc = 1.0;
+        if (nc > 256.0) nc = 256.0;
+        const int n = (int)nc;
+        g->ncells[k] = n;
+        g->periodic[k] = n >= 3 ? 1 : 0;
+        g->cs[4 * k] = edge[k] / (double)n;
+        total *= n;
+    }
+    g->ncell_total = total;
+}
+
 // Orthorhombic grid with a different minimum cell width per axis (rowfine.cuh: fine cells
 // along x, cutoff / 2 along y and z).
 static void grid_geometry_ortho_axes(const double *cutoff3, const float *L3, GridGeom *g)
@@ -544,11 +594,20 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     const uint64_t nbox = boxes_per_frame ? nframes : 1;
     std::vector<FrameGeom> fgs(nbox);
     int W = 0;                                  // 0: cell_tile_kernel on the reference grid
-    const int tiled = (!use_grid || force_basic == 1) ? 0 : (mic == MIC_ORTHO_LAZY ? 2 : (mic == MIC_TRICLINIC ? 1 : 0));
+    // triclinic cells: a finer grid (W = 2) only when the reference's own stencil is complete for
+    // every frame's cell (the pair set is then "every pair within the cutoff" on any complete grid)
+    bool tric_fine = mic == MIC_TRICLINIC && use_grid && box6 && h9 && !getenv("MDAGPU_RDF_NO_TRIC_FINE");
+    for (uint64_t f = 0; f < nbox && tric_fine; ++f) {
+        GridGeom gref;
+        float mc = 0.0f;
+        grid_geometry_reference(cutoff, box6 + 6 * f, h9 + 9 * f, 1, &gref, &mc);
+        if (!gref.triclinic || !tric_stencil_complete(gref, h9 + 9 * f, cutoff, 1)) tric_fine = false;
+    }
+    const int tiled = (!use_grid || force_basic == 1) ? 0 : (mic == MIC_ORTHO_LAZY ? 2 : (mic == MIC_TRICLINIC ? (tric_fine ? 2 : 1) : 0));
     // the packed kernels (rowfine.cuh, rowquad.cuh) fold the cutoff into the top histogram edge and
     // have no exclusion blocks
     const bool by_ids = ids_a_host != nullptr;
-    const bool packed_ok = tiled == 2 && !per_site && !by_ids && excl_a == 0 && r_hi > 0.0 && r_lo <= 0.0
+    const bool packed_ok = tiled == 2 && mic == MIC_ORTHO_LAZY && !per_site && !by_ids && excl_a == 0 && r_hi > 0.0 && r_lo <= 0.0
                            && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max && !getenv("MDAGPU_RDF_NO_QUAD");
     // ---- rowfine.cuh: fine cells along x (cutoff / WX), cutoff / 2 along y and z ----
     int fineWX = 0;
@@ -613,6 +672,10 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
                 MDA_REQUIRE(!(cutoff > (double)mc), "Cutoff %g too large for box (max %g)", cutoff, (double)mc);
                 if (tryW > 0 && mic == MIC_ORTHO_LAZY)
                     grid_geometry_ortho_free(cutoff / tryW, b6, nullptr, 1, &fg.grid);
+                if (tryW > 1 && mic == MIC_TRICLINIC) {
+                    grid_geometry_triclinic_free(cutoff, tryW, hh, &fg.grid);
+                    if (!tric_stencil_complete(fg.grid, hh, cutoff, tryW)) ok = false;
+                }
             } else {
                 grid_geometry_single(&fg.grid);
             }
@@ -626,6 +689,9 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
         }
         if (ok) W = tryW;
     }
+    if (getenv("MDAGPU_DEBUG"))
+        fprintf(stderr, "mdagpu: rdf traversal W = %d, fine x = %d, triclinic fine grid allowed = %d, grid %d x %d x %d\n", W, fineWX,
+                (int)tric_fine, fgs[0].grid.ncells[0], fgs[0].grid.ncells[1], fgs[0].grid.ncells[2]);
     const int64_t cells_per_frame = boxes_per_frame ? 0 : fgs[0].grid.ncell_total;
     // rowquad.cuh keeps one 32-bit histogram per warp of a 128-thread CTA
     const bool quad = packed_ok && W > 0 && (size_t)nbins * 4 * sizeof(uint32_t) <= 160 * 1024;
@@ -838,7 +904,10 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             MDA_CUDA(cudaStreamSynchronize(st));
             if (bad[0] | bad[1]) {
                 if (getenv("MDAGPU_DEBUG")) fprintf(stderr, "mdagpu: rdf cell list has folded atoms, piece of %llu frames\n", (unsigned long long)fc);
-                if (mic == MIC_TRICLINIC) tv.row = 0;
+                // (triclinic cells on the reference's own grid: its 27-cell per-pair kernel takes over in
+                // place; on a grid of the library's own -- orthorhombic, or triclinic with W = 2 -- the
+                // piece is recomputed on the reference's grid)
+                if (mic == MIC_TRICLINIC && W < 2) tv.row = 0;
                 else {
                     rc = rdf_accumulate_impl(a_dev, na, same ? nullptr : b_dev, nb, fc, boxes_per_frame ? box6 + 6 * f0 : box6,
                                              boxes_per_frame ? h9 + 9 * f0 : h9, boxes_per_frame, mic, wrap, cutoff, d2_max,

@@ -294,10 +294,15 @@ def test_qcp_trajectory_streamed_kernel(oracle, n, F, weighted):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["ortho_w2", "ortho_w2_ab", "ortho_w2_ab_excl", "ortho_w1", "ortho_w1_ab",
-                                  "ortho_perframe", "tric_w1", "tric_w1_ab", "tric_perframe", "tric_flat"])
+                                  "ortho_perframe", "tric_w1", "tric_w1_ab", "tric_perframe", "tric_flat",
+                                  "tric_w2", "tric_w2_ab", "tric_flat_dense", "tric_perframe_dense"])
 def test_interrdf_row_traversal(oracle, case):
     """The row-staged traversal (csrc/rowtile.cuh): every grid flavour it takes, against
-    the oracle's FastNS + np.histogram, bit-exact counts."""
+    the oracle's FastNS + np.histogram, bit-exact counts.  The dense triclinic cases have
+    enough atoms per cell for the library's own finer triclinic grid (W = 2, csrc/rdf.cu
+    grid_geometry_triclinic_free), which is only taken when the reference's 27-cell stencil is
+    complete for the cell (tric_stencil_complete): the 60/60/90 cell qualifies, the "flat" cells
+    (b_x c_y != 0: the reference misses pairs across the z boundary) must stay on its grid."""
     from mdanalysis_b200.analysis.rdf import InterRDF
     from mdanalysis_b200 import FrameBlock
     import zlib
@@ -316,10 +321,12 @@ def test_interrdf_row_traversal(oracle, case):
             dims[2, :3] *= 0.91
     else:
         N, rmax, nb = 7000, 6.0, 75
+        if case.startswith("tric_w2") or case.endswith("_dense"):
+            N = 24000
         dims = np.tile(np.array([60, 60, 60, 60, 60, 90], dtype=np.float32), (F, 1))
-        if case == "tric_flat":
+        if case.startswith("tric_flat"):
             dims[:] = np.array([70, 64, 58, 75, 100, 85], dtype=np.float32)
-        if case == "tric_perframe":
+        if case.startswith("tric_perframe"):
             dims[1] = np.array([64, 58, 66, 70, 80, 95], dtype=np.float32)
             dims[2, :3] *= 1.07
     pos = np.empty((F, N, 3), dtype=np.float32)
