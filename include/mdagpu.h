@@ -154,6 +154,12 @@ MDAGPU_API int mdagpu_grid_info(const mdagpu_grid *g, int *ncells3, double *cell
 /* geometry only (no coordinates), for callers that validate a cutoff */
 MDAGPU_API int mdagpu_grid_geometry(double cutoff, const float *box6, const float *h9, int pbc, int *ncells3,
                          double *cellsize9, int *periodic3, int *triclinic, float *max_cutoff);
+/* Host only, no GPU work.  Is the (2W + 1)^3 stencil COMPLETE on the grid FastNS builds for this box
+ * and cutoff, i.e. does FastNS (W = 1) return every pair within the cutoff?  (nsgrid.pyx:341-346
+ * elongates the cells by cutoff / sin(angle), which does not always cover the shear of its own cell
+ * coordinates, nsgrid.pyx:435-446.)  *complete = 0 or 1.  The triclinic InterRDF path leaves the
+ * reference's grid only for cells where this holds. */
+MDAGPU_API int mdagpu_grid_stencil_complete(double cutoff, const float *box6, const float *h9, int W, int *complete);
 MDAGPU_API void mdagpu_grid_free(mdagpu_grid *g);
 
 /* FastNS.search        nsgrid.pyx:499-580 : (query i, grid atom j) with d2 <= cutoff^2 */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mdagpu_grid_create": (_i, [_d, _vp, _u64, _vp, _vp, _i, _i, _vp, C.POINTER(_vp)]),
     "mdagpu_grid_info": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(C.c_float)]),
     "mdagpu_grid_geometry": (_i, [_d, _vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(C.c_float)]),
+    "mdagpu_grid_stencil_complete": (_i, [_d, _vp, _vp, _i, C.POINTER(_i)]),
     "mdagpu_grid_free": (None, [_vp]),
     "mdagpu_grid_search": (_i, [_vp, _vp, _u64, _i, _vp, C.POINTER(_vp)]),
     "mdagpu_grid_self_search": (_i, [_vp, _vp, C.POINTER(_vp)]),

@@ -564,6 +564,21 @@ struct HostPipe {
 
 using namespace mdagpu;
 
+extern "C" int mdagpu_grid_stencil_complete(double cutoff, const float *box6, const float *h9, int W, int *complete)
+{
+    MDA_REQUIRE(box6 && h9 && complete, "mdagpu_grid_stencil_complete: NULL argument");
+    MDA_REQUIRE(W >= 1, "mdagpu_grid_stencil_complete: W must be >= 1");
+    GridGeom g;
+    float mc = 0.0f;
+    grid_geometry_reference(cutoff, box6, h9, 1, &g, &mc);
+    bool ok = true;
+    for (int k = 0; k < 3; ++k) ok = ok && g.periodic[k];          // (a non-periodic axis is one cell: complete, but not this test's business)
+    *complete = (ok && (g.triclinic ? tric_stencil_complete(g, h9, cutoff, W)
+                                     : (W * g.cs[0] >= cutoff && W * g.cs[4] >= cutoff && W * g.cs[8] >= cutoff))) ? 1 : 0;
+    return MDAGPU_OK;
+}
+
+
 static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint64_t nb,
                                uint64_t nframes, const float *box6, const float *h9,
                                int boxes_per_frame, int mic, int wrap, double cutoff,
