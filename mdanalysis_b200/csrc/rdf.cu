@@ -381,9 +381,9 @@ static int launch_hist(const CellList &ql, const CellList &cl, const FrameGeom *
     dim3 grid((unsigned)tv.grid_x, (unsigned)nframes);
     if constexpr (Sink::THREADS == 224) {
         // the 224-thread sink exists for the packed kernel only (a whole row of home cells per CTA)
-        if constexpr (MIC == MIC_ORTHO_LAZY) {
+        if constexpr (MIC == MIC_ORTHO_LAZY || MIC == MIC_TRICLINIC) {
             if (tv.row && tv.quad) {
-                auto kern = row_quad_kernel<SELF, Sink, WQ_CAP_224, 4>;
+                auto kern = row_quad_kernel<SELF, Sink, WQ_CAP_224, 4, MIC>;
                 const size_t total = ((smem + 15) & ~(size_t)15) + 3 * (size_t)WQ_CAP_224 * sizeof(float);
                 MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
                 MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, Sink::THREADS, total, st, ql.atoms(), ql.start(),
@@ -394,9 +394,9 @@ static int launch_hist(const CellList &ql, const CellList &cl, const FrameGeom *
         }
         return set_error(MDAGPU_ERR_INVALID, "internal: 224-thread histogram sink without the packed kernel");
     } else {
-    if constexpr (MIC == MIC_ORTHO_LAZY && std::is_same<Sink, HistSink<128, false>>::value) {
+    if constexpr ((MIC == MIC_ORTHO_LAZY || MIC == MIC_TRICLINIC) && std::is_same<Sink, HistSink<128, false>>::value) {
         if (tv.row && tv.quad) {
-            auto kern = row_quad_kernel<SELF, Sink, WQ_CAP_128, 7>;
+            auto kern = row_quad_kernel<SELF, Sink, WQ_CAP_128, 7, MIC>;
             const size_t total = ((smem + 15) & ~(size_t)15) + 3 * (size_t)WQ_CAP_128 * sizeof(float);
             if (total > 24 * 1024)
                 MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
@@ -622,8 +622,12 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
     // the packed kernels (rowfine.cuh, rowquad.cuh) fold the cutoff into the top histogram edge and
     // have no exclusion blocks
     const bool by_ids = ids_a_host != nullptr;
-    const bool packed_ok = tiled == 2 && mic == MIC_ORTHO_LAZY && !per_site && !by_ids && excl_a == 0 && r_hi > 0.0 && r_lo <= 0.0
-                           && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max && !getenv("MDAGPU_RDF_NO_QUAD");
+    const bool packed_any = tiled == 2 && !per_site && !by_ids && excl_a == 0 && r_hi > 0.0 && r_lo <= 0.0
+                            && fabs(d2_max - r_hi * r_hi) <= 1e-12 * d2_max && !getenv("MDAGPU_RDF_NO_QUAD");
+    const bool packed_ok = packed_any && mic == MIC_ORTHO_LAZY;
+    // triclinic cells: the packed kernel on the library's own grid (W = 2) only -- on the reference's
+    // grid a lane's cell window is part of the result
+    const bool packed_tric = packed_any && mic == MIC_TRICLINIC && !getenv("MDAGPU_RDF_NO_TRIC_QUAD");
     // ---- rowfine.cuh: fine cells along x (cutoff / WX), cutoff / 2 along y and z ----
     int fineWX = 0;
     float fine_reach = 0.0f;
@@ -709,7 +713,7 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
                 (int)tric_fine, fgs[0].grid.ncells[0], fgs[0].grid.ncells[1], fgs[0].grid.ncells[2]);
     const int64_t cells_per_frame = boxes_per_frame ? 0 : fgs[0].grid.ncell_total;
     // rowquad.cuh keeps one 32-bit histogram per warp of a 128-thread CTA
-    const bool quad = packed_ok && W > 0 && (size_t)nbins * 4 * sizeof(uint32_t) <= 160 * 1024;
+    const bool quad = ((packed_ok && W > 0) || (packed_tric && W == 2)) && (size_t)nbins * 4 * sizeof(uint32_t) <= 160 * 1024;
     // error of the FP32 distance estimate for the row traversals (per-cell-pair image prediction)
     // and for the per-pair traversals the code falls back to (27-image FP32 scan for triclinic cells)
     double err_row = 0.0, err_cell = 0.0;

@@ -22,8 +22,11 @@
 //    harmless: an atom outside the lane's cells [cell - W, cell + W] is farther than the
 //    cutoff under the image of its run (cells are >= cutoff / W * (1 + 1e-4) + 1e-3 wide,
 //    rdf.cu: grid_geometry_ortho_free) and fails the range test like any distant atom.
-//    (Not so for triclinic cells, where the reference's own stencil can be incomplete and
-//    the window is part of the result: those stay on rowtile.cuh.)
+//    (Not so on the REFERENCE's grid for triclinic cells, where its own stencil can be
+//    incomplete and the window is part of the result: those stay on rowtile.cuh.  On the
+//    library's own triclinic grid -- rdf.cu: grid_geometry_triclinic_free, taken only where
+//    the reference's stencil is complete -- the same argument holds and this kernel runs with
+//    MIC = MIC_TRICLINIC: the row's translation is ib b + ic c, all three components.)
 //  * The cutoff is the top histogram edge (InterRDF passes range[1] as max_cutoff,
 //    rdf.py:270-272), so "inside the cutoff" is "bin coordinate below nbins" and the band
 //    around the cutoff is the band around the last edge: one range test, one band test.
@@ -54,7 +57,12 @@ static inline double rowquad_abs_err(const BoxParams &b, double cutoff)
 {
     double s = 0.0;
     for (int k = 0; k < 3; ++k) {
-        const double e = (3.0 * fabs((double)b.L[k]) + 2.0 * cutoff) * 6e-8;
+        // triclinic cells: S = sum of the lattice components along the axis bounds a wrapped
+        // coordinate; t = fl(ib b + ic c) (S), q' = fl(q - t) (2 S), fl(q' +- a) (3 S), the
+        // reference's own fl(q - c) (S): 7 S + cutoff, rounded up
+        const double e = b.mode == BOX_TRICLINIC
+            ? (8.0 * (fabs((double)b.h[k]) + fabs((double)b.h[3 + k]) + fabs((double)b.h[6 + k])) + 2.0 * cutoff) * 6e-8
+            : (3.0 * fabs((double)b.L[k]) + 2.0 * cutoff) * 6e-8;
         s += e * e;
     }
     return sqrt(s);
@@ -186,13 +194,13 @@ __device__ __forceinline__ void quad_walk(uint32_t planes, uint32_t qa, uint32_t
 
 // Exact evaluation of one queued pair (slots in the sorted arrays) in the reference's
 // float64 arithmetic; the histogram sink bins it against the exact thresholds.
-template <bool SELF, class Sink>
+template <bool SELF, class Sink, int MIC = MIC_ORTHO_LAZY>
 __device__ __noinline__ void quad_exact(Sink sink, const BoxParams *box, double d2_max, double d2_min,
                                         const float4 *__restrict__ q_atoms, const float4 *__restrict__ c_atoms,
                                         uint32_t qslot, uint32_t cslot, uint64_t f)
 {
     const float4 q = q_atoms[qslot], c = c_atoms[cslot];
-    const double d2 = pair_d2_exact<MIC_ORTHO_LAZY>(q.x, q.y, q.z, c.x, c.y, c.z, *box);
+    const double d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, c.x, c.y, c.z, *box);
     if (d2 <= d2_max && d2 > d2_min) sink.template hit_w<SELF>(__float_as_int(q.w), __float_as_int(c.w), d2, f);
 }
 
@@ -201,21 +209,22 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <bool SELF, class Sink, int CAP, int MIN_CTAS>
+template <bool SELF, class Sink, int CAP, int MIN_CTAS, int MIC_ = MIC_ORTHO_LAZY>
 __global__ void __launch_bounds__(Sink::THREADS, MIN_CTAS)
 row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
                 const float4 *__restrict__ c_atoms, const uint32_t *__restrict__ c_start,
                 const FrameGeom *__restrict__ fgs, int per_frame, RowParams rp, SearchParams sp, Sink sink)
 {
     constexpr int T = Sink::THREADS, NW = T / 32;
-    constexpr int MIC = MIC_ORTHO_LAZY;
+    constexpr int MIC = MIC_;
+    static_assert(MIC == MIC_ORTHO_LAZY || MIC == MIC_TRICLINIC, "cells with a periodic image per cell pair");
     __shared__ RowBook bk;
     // x, y, z planes of the staged rows: dynamic shared memory behind the per-warp histograms
     extern __shared__ __align__(16) unsigned char quad_dyn[];
     float *tile = reinterpret_cast<float *>(quad_dyn + (((size_t)sink.nbins * NW * sizeof(uint32_t) + 15) & ~(size_t)15));
     __shared__ uint32_t s_base[ROW_MAXROWS + 1];                   // padded tile coordinate where each row starts
     __shared__ uint4 s_pad[ROW_MAXROWS];                           // {P1, P2, P3, -}: padded starts of runs 1, 2 and the row's end
-    __shared__ float2 s_shift[ROW_MAXROWS];                        // the row's lattice translation (y, z)
+    __shared__ float4 s_shift[ROW_MAXROWS];                        // the row's lattice translation (x is 0 for orthorhombic cells)
     __shared__ uint2 s_slow[NW][WQ_SLOW];                          // queued (query slot, candidate slot)
     __shared__ uint32_t s_nslow[NW];
     __shared__ uint32_t s_trash[T];
@@ -238,12 +247,16 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
     if (job.empty) return;
     const int W = job.W, nh = job.nh, NC = job.NC, nrows = job.nrows;
     const BoxParams &box = bk.fg.box;
-    const float Lx = box.L[0], Ly = box.L[1], Lz = box.L[2];
+    const float Lx = MIC == MIC_TRICLINIC ? box.h[0] : box.L[0];   // a = (a_x, 0, 0) in either case
     const uint32_t qs0 = bk.qst[0], qs1 = bk.qst[nh];
     for (int r = tid; r < nrows; r += T) {
         const QuadPad qp = quad_pad(bk.row[r]);
         s_pad[r] = make_uint4(qp.P[1], qp.P[2], qp.P[3], 0u);
-        s_shift[r] = make_float2((float)bk.row[r].ib * Ly, (float)bk.row[r].ic * Lz);
+        const float fb = (float)bk.row[r].ib, fc = (float)bk.row[r].ic;
+        if (MIC == MIC_TRICLINIC)                                  // ib b + ic c
+            s_shift[r] = make_float4(fb * box.h[3] + fc * box.h[6], fb * box.h[4] + fc * box.h[7], fb * box.h[5] + fc * box.h[8], 0.0f);
+        else
+            s_shift[r] = make_float4(0.0f, fb * box.L[1], fc * box.L[2], 0.0f);
     }
     __syncthreads();
     QuadConst kc = s_kc;
@@ -259,7 +272,7 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
         const uint32_t n = min(*nslow, (uint32_t)WQ_SLOW);
         for (uint32_t i = lane; i < n; i += 32) {
             const uint2 e = slowq[i];
-            quad_exact<SELF, Sink>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, e.x, e.y, f);
+            quad_exact<SELF, Sink, MIC>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, e.x, e.y, f);
         }
         __syncwarp();
         if (lane == 0) *nslow = 0u;
@@ -361,8 +374,9 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
                     const uint32_t p_hi = (r == r0 && piece) ? c0 + piece : pd.z;
                     const uint32_t planes = tile0 + 4u * s_base[r];
                     // the row's lattice translation goes onto the query: q - (c + t) = (q - t) - c
-                    const float2 sh = s_shift[r];
-                    const float qy = q.y - sh.x, qz = q.z - sh.y;
+                    const float4 sh = s_shift[r];
+                    const float qxr = MIC == MIC_TRICLINIC ? q.x - sh.x : q.x;
+                    const float qy = q.y - sh.y, qz = q.z - sh.z;
 #pragma unroll 1
                     for (int s = 0; s < 3; ++s) {
                         const uint32_t sb = s ? ri.end[s - 1] : 0u, se = ri.end[s];
@@ -373,14 +387,14 @@ row_quad_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__
                         const uint32_t ta = max(a + shift, p_lo), te = min(e + shift, p_hi);
                         if (ta >= te) continue;
                         const uint32_t qa = (ta - p_lo) >> 2, qe = (te - p_lo + 3u) >> 2;
-                        const float qx = q.x + (float)(1 - s) * Lx; // left run: image -Lx, i.e. q + Lx
+                        const float qx = qxr + (float)(1 - s) * Lx; // left run: image -a, i.e. q + a
                         // a pair inside a band: padded -> global slot (a sentinel is never inside one)
                         const uint32_t g0 = ri.g[s] + p_lo - P;
                         auto slow_fn = [&](uint32_t quad, int k) {
                             const uint32_t cslot = g0 + 4u * quad + (uint32_t)k;
                             const uint32_t at = atomicAdd(nslow, 1u);
                             if (at < (uint32_t)WQ_SLOW) slowq[at] = make_uint2(qslot, cslot);
-                            else quad_exact<SELF, Sink>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, qslot, cslot, f);
+                            else quad_exact<SELF, Sink, MIC>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, qslot, cslot, f);
                         };
                         // home row, in-range run: only candidates behind the query itself
                         // (padded == row coordinate there: the left run of a home row is empty)
