@@ -117,7 +117,8 @@ def ncu_traffic(n_frames, n_atoms):
             t = json.load(fh)
         per_atom = (t["dram_bytes_read"] + t["dram_bytes_write"]) / (t["frames_per_launch"] * t["atoms"])
         return {"dram_bytes_per_launch": per_atom * n_frames * n_atoms, "unit": "B",
-                "algorithmic_bytes_per_launch": 16.0 * n_frames * n_atoms, "source": t["source"]}
+                "algorithmic_bytes_per_launch": 16.0 * n_frames * n_atoms, "source": t["source"],
+                "note": t.get("note")}
     except (OSError, KeyError, ValueError):
         return None
 

@@ -48,6 +48,27 @@ def sqrt_le_threshold(e):
 
 
 _THRESHOLD_CACHE = {}
+_EDGE_CACHE = {}
+
+
+def histogram_edges(settings):
+    """``np.histogram([-1], **settings)`` as the reference calls it for its bin edges
+    (analysis/rdf.py:253-257): ``(number of bins, edges)``, cached per setting (the call costs
+    0.12 ms, a visible share of a short run)."""
+    try:
+        key = (settings["bins"] if np.isscalar(settings["bins"]) else None, tuple(map(float, settings["range"])))
+    except (KeyError, TypeError, ValueError):
+        key = (None,)
+    if key[0] is None:
+        count, edges = np.histogram([-1], **settings)
+        return len(count), edges
+    hit = _EDGE_CACHE.get(key)
+    if hit is None:
+        count, edges = np.histogram([-1], **settings)
+        if len(_EDGE_CACHE) > 64:
+            _EDGE_CACHE.clear()
+        hit = _EDGE_CACHE[key] = (len(count), edges)
+    return hit[0], hit[1].copy()
 
 
 def histogram_thresholds(edges):
@@ -152,10 +173,8 @@ class InterRDF(BlockAnalysis):
         return super().run(start, stop, step, frames, **kwargs)
 
     def _prepare(self, blk):
-        count, edges = np.histogram([-1], **self.rdf_settings)
-        count = count.astype(np.float64)
-        count *= 0.0
-        self.results.count = count
+        ncount, edges = histogram_edges(self.rdf_settings)
+        self.results.count = np.zeros(ncount, dtype=np.float64)
         self.results.edges = edges
         self.results.bins = 0.5 * (edges[:-1] + edges[1:])
         self.volume_cum = 0
@@ -327,8 +346,8 @@ class InterRDF_s(BlockAnalysis):
             self.norm = "density"
 
     def _prepare(self, blk):
-        count, edges = np.histogram([-1], **self.rdf_settings)
-        self.results.count = [np.zeros((len(a), len(b), len(count)), dtype=np.float64) for a, b in self.ags]
+        ncount, edges = histogram_edges(self.rdf_settings)
+        self.results.count = [np.zeros((len(a), len(b), ncount), dtype=np.float64) for a, b in self.ags]
         self.results.edges = edges
         self.results.bins = 0.5 * (edges[:-1] + edges[1:])
         self.volume_cum = 0
