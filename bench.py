@@ -481,6 +481,13 @@ def bench_c2(ctx):
               "note": "the stated 1000 frames split with np.array_split; one all_reduce of [count, volume, frames] per step; "
                       "what does not shrink with N is the host side of run() (launch + Python) and the collective"}
 
+    # hits/s and candidates/s next to frames/s.  A hit = an ordered pair inside
+    # the cutoff = what the histogram holds (self pairs included); candidates = the 1760 per query of the
+    # cell = r_c / 2 traversal the algorithmic flop count is defined on (the fine-x walk evaluates ~550).
+    hits_per_frame = float(np.sum(result["rdf"].results.count)) / (F * (ctx.world if ctx.dist_ready else 1))
+    roofline["hits_per_s"] = hits_per_frame * value
+    roofline["hits_per_frame"] = hits_per_frame
+    roofline["algorithmic_candidates_per_s"] = (ALGO_FLOP_PER_FRAME / 11.0) * (N / N_O) ** 2 * value
     cpu_baseline = None
     if ctx.cpu:
         from oracle import oracle as orc
