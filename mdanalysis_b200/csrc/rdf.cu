@@ -674,6 +674,90 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             if (ok) { fineWX = wx; fine_reach = (float)reach; W = 2; }
         }
     }
+    // ---- rowfine.cuh for triclinic cells: the same traversal in the cell coordinates of cell_of() ----
+    // Only where the reference's own stencil is complete (tric_fine: the pair set is then "every pair
+    // within the cutoff") and the lattice images are whole grids in cell coordinates (t_xy c_y = 0).
+    bool fine_tric = false;
+    if (!fineWX && packed_tric && tric_fine && force_basic != 2 && !getenv("MDAGPU_RDF_NO_FINE")
+        && !getenv("MDAGPU_RDF_NO_TRIC_FINE_X")) {
+        const int choices[2] = { 8, 4 };
+        for (int ci = 0; ci < 2 && !fineWX; ++ci) {
+            const int wx = choices[ci];
+            bool ok = true;
+            int64_t base = 0;
+            double reach = 0.0;
+            for (uint64_t f = 0; f < nbox && ok; ++f) {
+                FrameGeom &fg = fgs[f];
+                const float *hh = h9 + 9 * f;
+                fg.box = make_box_params(BOX_TRICLINIC, hh);
+                float mc = 0.0f;
+                grid_geometry_reference(cutoff, box6 + 6 * f, hh, 1, &fg.grid, &mc);
+                MDA_REQUIRE(!(cutoff > (double)mc), "Cutoff %g too large for box (max %g)", cutoff, (double)mc);
+                GridGeom &g = fg.grid;
+                g.triclinic = 1;
+                g.pbc = 1;
+                for (int k = 0; k < 9; ++k) g.cs[k] = 0.0;
+                g.origin[0] = g.origin[1] = g.origin[2] = 0.0;
+                g.cs[3] = (double)(hh[3] / hh[4]);
+                g.cs[6] = (double)(hh[6] / hh[8]);
+                g.cs[7] = (double)(hh[7] / hh[8]);
+                if (fabs(g.cs[3] * (double)hh[7]) > 1e-7 * (double)hh[0]) ok = false;
+                double lmax = 0.0;
+                for (int k = 0; k < 3; ++k)
+                    lmax = fmax(lmax, fabs((double)hh[k]) + fabs((double)hh[3 + k]) + fabs((double)hh[6 + k]));
+                // margin of the per-lane windows: cell coordinates and interval ends evaluated in FP32
+                // from box-sized values
+                const double rch = cutoff * (1.0 + 2e-5) + 1e-4 + 1.2e-5 * lmax;
+                reach = fmax(reach, rch);
+                const double fxx = sqrt(1.0 + g.cs[3] * g.cs[3] + g.cs[6] * g.cs[6]), fyy = sqrt(1.0 + g.cs[7] * g.cs[7]);
+                const double need[3] = { rch * fxx / wx, rch * fyy / 2.0, rch / 2.0 };
+                const double edge[3] = { (double)hh[0], (double)hh[4], (double)hh[8] };
+                const int w3[3] = { wx, 2, 2 };
+                int64_t total = 1;
+                for (int k = 0; k < 3; ++k) {
+                    double nc = floor(edge[k] / (need[k] * (1.0 + 1e-4) + 1e-3));
+                    if (!(nc >= 1.0)) nc = 1.0;
+                    if (nc > 256.0) nc = 256.0;
+                    g.ncells[k] = (int)nc;
+                    g.periodic[k] = g.ncells[k] >= 3 ? 1 : 0;
+                    g.cs[4 * k] = edge[k] / (double)g.ncells[k];
+                    total *= g.ncells[k];
+                    if (!g.periodic[k] || g.ncells[k] < 2 * w3[k] + 2) ok = false;
+                }
+                g.ncell_total = total;
+                // one image per window: perpendicular widths as in rowtile_supported(), with the
+                // stencil half-width of each axis
+                if (ok) {
+                    const double h0[3] = { hh[0], hh[1], hh[2] }, h1[3] = { hh[3], hh[4], hh[5] }, h2[3] = { hh[6], hh[7], hh[8] };
+                    auto cross = [](const double *u, const double *v, double *o) {
+                        o[0] = u[1] * v[2] - u[2] * v[1]; o[1] = u[2] * v[0] - u[0] * v[2]; o[2] = u[0] * v[1] - u[1] * v[0];
+                    };
+                    auto norm = [](const double *u) { return sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]); };
+                    double c12[3], c20[3], c01[3];
+                    cross(h1, h2, c12); cross(h2, h0, c20); cross(h0, h1, c01);
+                    const double vol = fabs(h0[0] * c12[0] + h0[1] * c12[1] + h0[2] * c12[2]);
+                    const double width[3] = { vol / norm(c12), vol / norm(c20), vol / norm(c01) };
+                    for (int k = 0; k < 3; ++k) {
+                        if (!(width[k] > 2.0 * rch * (1.0 + 1e-5))) ok = false;
+                        if (!((1.0 - (double)(w3[k] + 1) / g.ncells[k]) * width[k] > rch * (1.0 + 1e-5))) ok = false;
+                    }
+                    // a window reaches at most wx cells into the halo that is staged on either side
+                    if (!((double)wx * g.cs[0] >= rch * fxx)) ok = false;
+                }
+                {
+                    const double inv = (double)nbins / (r_hi - r_lo);
+                    const double u_err = (4e-7 * fmax(fabs(r_hi), fabs(r_lo)) + rowquad_abs_err(fg.box, cutoff)) * inv
+                                         + 2e-7 * (fabs(-r_lo * inv - 0.5) + (double)nbins);
+                    if (!(fmax(5e-4, 2.0 * u_err) < 0.2)) ok = false;
+                    if ((size_t)(nbins + 2) * sizeof(uint32_t) > 20 * 1024) ok = false;
+                }
+                if ((double)nb / (double)g.ncell_total < (wx == 8 ? 1.5 : 0.75)) ok = false;
+                fg.cell_base = base;
+                base += g.ncell_total;
+            }
+            if (ok) { fineWX = wx; fine_reach = (float)reach; W = 2; fine_tric = true; }
+        }
+    }
     for (int tryW = tiled; tryW >= 0 && W == 0; --tryW) {
         int64_t base = 0;
         bool ok = tryW > 0;
@@ -980,16 +1064,18 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             MDA_CUDA(cudaMemsetAsync(oflag.p, 0, sizeof(unsigned), st));
             dim3 grid((unsigned)units_x, (unsigned)fc);
             const size_t plan_smem = (size_t)nrows * (size_t)(R + 2 * fineWX + 1) * sizeof(uint32_t);
-            if (same)
-                MDA_LAUNCH_AS("rdf_window_planner", (fine_plan_kernel<true, 224>), grid, 224, plan_smem, st, cl.atoms(), cl.start(),
-                              cl.start(), fgd, boxes_per_frame, fgs[boxes_per_frame ? f0 : 0], fp, RF_CAP, list_cap,
-                              units.as<FineUnit<13>>(), lists.as<uint32_t>(), oflag.as<unsigned>(), cl.inconsistent(),
-                              (const unsigned *)nullptr);
-            else
-                MDA_LAUNCH_AS("rdf_window_planner", (fine_plan_kernel<false, 224>), grid, 224, plan_smem, st, ql.atoms(), ql.start(),
-                              cl.start(), fgd, boxes_per_frame, fgs[boxes_per_frame ? f0 : 0], fp, RF_CAP, list_cap,
-                              units.as<FineUnit<25>>(), lists.as<uint32_t>(), oflag.as<unsigned>(), cl.inconsistent(),
-                              ql.inconsistent());
+#define FINE_PLAN(SELF_, MIC_, QL_, NR_, BAD1_)                                                                  \
+    MDA_LAUNCH_AS("rdf_window_planner", (fine_plan_kernel<SELF_, 224, MIC_>), grid, 224, plan_smem, st, QL_.atoms(), QL_.start(), \
+                  cl.start(), fgd, boxes_per_frame, fgs[boxes_per_frame ? f0 : 0], fp, RF_CAP, list_cap,          \
+                  units.as<FineUnit<NR_>>(), lists.as<uint32_t>(), oflag.as<unsigned>(), cl.inconsistent(), BAD1_)
+            if (same) {
+                if (fine_tric) FINE_PLAN(true, MIC_TRICLINIC, cl, 13, (const unsigned *)nullptr);
+                else FINE_PLAN(true, MIC_ORTHO_LAZY, cl, 13, (const unsigned *)nullptr);
+            } else {
+                if (fine_tric) FINE_PLAN(false, MIC_TRICLINIC, ql, 25, ql.inconsistent());
+                else FINE_PLAN(false, MIC_ORTHO_LAZY, ql, 25, ql.inconsistent());
+            }
+#undef FINE_PLAN
             MDA_CHECK_LAUNCH();
             // lane columns of the histogram: 16 keep four CTAs on an SM (55 kB each)
             int ls = 4;
@@ -999,35 +1085,35 @@ static int rdf_accumulate_impl(const float *A, uint64_t na, const float *B, uint
             const size_t hist = ((((size_t)(nbins + 2) << ls) * sizeof(uint32_t)) + 15) & ~(size_t)15;
             const size_t total = hist + 3 * (size_t)RF_CAP * sizeof(float);
             // (per device and cheap: set on every call, like the other kernels of this file)
-            if (same)
-                MDA_CUDA(cudaFuncSetAttribute(fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
-            else
-                MDA_CUDA(cudaFuncSetAttribute(fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
             const BoxParams bx = fgs[boxes_per_frame ? f0 : 0].box;
             // (per-frame boxes: the walker only needs the box for the rare float64 evaluations; frames of
             // one call that differ in their box are binned frame by frame)
-            if (boxes_per_frame) {
-                for (uint64_t ff = 0; ff < fc; ++ff) {
-                    dim3 g1((unsigned)units_x, 1u);
-                    const BoxParams bxf = fgs[f0 + ff].box;
-                    if (same)
-                        MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>), g1, 224, total, st,
-                                      cl.atoms(), cl.atoms(), units.as<FineUnit<13>>() + ff * units_x,
-                                      lists.as<uint32_t>() + ff * units_x * list_cap, list_cap, bxf, spc, sink, oflag.as<unsigned>(), cl.inconsistent(), same ? (const unsigned *)nullptr : ql.inconsistent());
-                    else
-                        MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>), g1, 224, total, st,
-                                      ql.atoms(), cl.atoms(), units.as<FineUnit<25>>() + ff * units_x,
-                                      lists.as<uint32_t>() + ff * units_x * list_cap, list_cap, bxf, spc, sink, oflag.as<unsigned>(), cl.inconsistent(), same ? (const unsigned *)nullptr : ql.inconsistent());
-                }
-            } else if (same) {
-                MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<true, HistSinkFine<224>, RF_CAP, 4>), grid, 224, total, st,
-                              cl.atoms(), cl.atoms(), units.as<FineUnit<13>>(), lists.as<uint32_t>(), list_cap, bx, spc, sink, oflag.as<unsigned>(), cl.inconsistent(), (const unsigned *)nullptr);
+#define FINE_WALK(SELF_, MIC_, QL_, NR_, BAD2_)                                                                  \
+    do {                                                                                                        \
+        auto kern = fine_walk_kernel<SELF_, HistSinkFine<224>, RF_CAP, 4, MIC_>;                                 \
+        MDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));           \
+        if (boxes_per_frame) {                                                                                  \
+            for (uint64_t ff = 0; ff < fc; ++ff) {                                                              \
+                dim3 g1((unsigned)units_x, 1u);                                                                 \
+                const BoxParams bxf = fgs[f0 + ff].box;                                                         \
+                MDA_LAUNCH_AS("rdf_pair_histogram", kern, g1, 224, total, st, QL_.atoms(), cl.atoms(),          \
+                              units.as<FineUnit<NR_>>() + ff * units_x, lists.as<uint32_t>() + ff * units_x * list_cap, \
+                              list_cap, bxf, spc, sink, oflag.as<unsigned>(), cl.inconsistent(), BAD2_);         \
+            }                                                                                                   \
+        } else {                                                                                                \
+            MDA_LAUNCH_AS("rdf_pair_histogram", kern, grid, 224, total, st, QL_.atoms(), cl.atoms(),            \
+                          units.as<FineUnit<NR_>>(), lists.as<uint32_t>(), list_cap, bx, spc, sink,              \
+                          oflag.as<unsigned>(), cl.inconsistent(), BAD2_);                                       \
+        }                                                                                                       \
+    } while (0)
+            if (same) {
+                if (fine_tric) FINE_WALK(true, MIC_TRICLINIC, cl, 13, (const unsigned *)nullptr);
+                else FINE_WALK(true, MIC_ORTHO_LAZY, cl, 13, (const unsigned *)nullptr);
             } else {
-                MDA_LAUNCH_AS("rdf_pair_histogram", (fine_walk_kernel<false, HistSinkFine<224>, RF_CAP, 4>), grid, 224, total, st,
-                              ql.atoms(), cl.atoms(), units.as<FineUnit<25>>(), lists.as<uint32_t>(), list_cap, bx, spc, sink, oflag.as<unsigned>(), cl.inconsistent(), ql.inconsistent());
+                if (fine_tric) FINE_WALK(false, MIC_TRICLINIC, ql, 25, ql.inconsistent());
+                else FINE_WALK(false, MIC_ORTHO_LAZY, ql, 25, ql.inconsistent());
             }
+#undef FINE_WALK
             MDA_CHECK_LAUNCH();
             {
                 // flags of this piece -> pinned slot; looked at after the NEXT piece has been queued

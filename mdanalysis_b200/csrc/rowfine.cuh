@@ -28,6 +28,16 @@
 //    two LOP3 and one branch per four candidates); it is taken OUT of the bin the FP32
 //    path put it into and queued for the float64 evaluation.
 //  * 48 issue slots per four candidates (was 61).
+//  * Triclinic cells (MIC = MIC_TRICLINIC; only on the library's own grid, where the reference's
+//    stencil is complete, rdf.cu).  The walk is Cartesian and needs nothing but the row's full
+//    translation ib b + ic c on the query.  The planner works in the cell coordinates of
+//    geom.cuh cell_of(): x' = (x - t_xy y - t_xz z) / cs_xx, y' = (y - t_yz z) / cs_yy,
+//    z' = z / cs_zz, in which the lattice images are whole grids (t_xy c_y = 0 is required), a
+//    stencil row is the unit square [dy, dy + 1) x [dz, dz + 1) relative to the query's cell,
+//    and the Cartesian separation of a pair is dz = cs_zz dz', dy = cs_yy dy' + t_yz dz,
+//    dx = cs_xx dx' + t_xy dy + t_xz dz.  Interval arithmetic over the square gives the gaps
+//    (-> h as before) and the range of the shear t_xy dy + t_xz dz, by which the window in x'
+//    is widened: [x' + (-h - s_max) / cs_xx, x' + (h - s_min) / cs_xx].
 #pragma once
 #include "rowquad.cuh"
 
@@ -195,7 +205,7 @@ __device__ __forceinline__ void fine_walk2(uint32_t planes, uint32_t qa, uint32_
 // ---- planner -> walker hand-over (global scratch), one unit per (frame, (y, z) row, x segment) ----
 struct FineRowA { uint32_t g0, g1, g2, base; };                    // global slot of the first atom of each run; tile position of the row
 struct FineRowB { uint32_t end0, end1, len, pad; };                // extended positions where the runs end; staged candidates
-struct FineRowC { float sy, sz, xl, pad; };                        // lattice translation of the row (y, z); box edge along x
+struct FineRowC { float sy, sz, xl, sx; };                         // lattice translation of the row (y, z; x for triclinic cells); box edge along x
 struct FineUnitHead {
     uint32_t nrec, hstart;      // window records; where the home-row records start (a multiple of 32)
     uint32_t qs0, nq;           // first query slot, queries
@@ -217,7 +227,7 @@ constexpr unsigned FINE_OVER_TILE = 2u, FINE_OVER_LIST = 4u, FINE_OVER_QUERIES =
 // 73 000 cycles per CTA): row descriptors, and the (pair of queries, row) windows as records
 //   quads | first quad << 7 | pair << 17 | row << 25
 // counting-sorted by length, longest first, home-row records behind the others.
-template <bool SELF, int T>
+template <bool SELF, int T, int MIC = MIC_ORTHO_LAZY>
 __global__ void __launch_bounds__(T, 6)
 fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict__ q_start,
                  const uint32_t *__restrict__ c_start, const FrameGeom *__restrict__ fgs, int per_frame,
@@ -349,7 +359,11 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                                    dz > 0 ? (float)(z + dz) * wz : (dz < 0 ? -(float)(z + dz + 1) * wz : 0.0f));
             unit.a[r] = { s_raw[r][0], s_raw[r][1], s_raw[r][2], incl - mine };
             unit.b[r] = { nL, nL + nM, len, 0u };
-            unit.c[r] = { (float)ib * box.L[1], (float)ic * box.L[2], box.L[0], 0.0f };
+            if (MIC == MIC_TRICLINIC)                               // ib b + ic c; a = (h0, 0, 0)
+                unit.c[r] = { (float)ib * box.h[4] + (float)ic * box.h[7], (float)ic * box.h[8], box.h[0],
+                              (float)ib * box.h[3] + (float)ic * box.h[6] };
+            else
+                unit.c[r] = { (float)ib * box.L[1], (float)ic * box.L[2], box.L[0], 0.0f };
         }
     }
     const int ne1 = next + 1;
@@ -404,6 +418,42 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
             lo = eo[e0 + WX - k];
             hi = h2 > 0.0f ? eo[e0 + WX + k + 1] : lo;
         };
+        // triclinic cells: the query in cell coordinates (see the head of the file)
+        const float t_xy = (float)s_fg.grid.cs[3], t_xz = (float)s_fg.grid.cs[6], t_yz = (float)s_fg.grid.cs[7];
+        const float inv_wy = (float)(1.0 / s_fg.grid.cs[4]), inv_wz = (float)(1.0 / s_fg.grid.cs[8]);
+        const float wx_f = (float)s_fg.grid.cs[0];
+        struct CellPos { float xc, fy, fz; };
+        auto cell_pos = [&](const float4 &qq) {
+            CellPos c;
+            c.fz = qq.z * inv_wz - (float)z;
+            c.fy = (qq.y - t_yz * qq.z) * inv_wy - (float)y;
+            c.xc = (qq.x - t_xy * qq.y - t_xz * qq.z) * inv_wx;
+            return c;
+        };
+        const CellPos cpa = MIC == MIC_TRICLINIC ? cell_pos(q) : CellPos{ 0.f, 0.f, 0.f };
+        const CellPos cpb = MIC == MIC_TRICLINIC ? cell_pos(qb) : CellPos{ 0.f, 0.f, 0.f };
+        auto window_tri = [&](const CellPos &c, int dy, int dz, const uint32_t *eo, uint32_t &lo, uint32_t &hi) {
+            // Cartesian dz, dy over the row's unit square
+            const float zlo = wz * ((float)dz - c.fz), zhi = zlo + wz;
+            const float ya = wy * ((float)dy - c.fy);
+            const float ylo = ya + fminf(t_yz * zlo, t_yz * zhi), yhi = ya + wy + fmaxf(t_yz * zlo, t_yz * zhi);
+            const float gz = fmaxf(0.0f, fmaxf(zlo, -zhi)), gy = fmaxf(0.0f, fmaxf(ylo, -yhi));
+            const float h2 = fmaf(-gy, gy, fmaf(-gz, gz, reach2));
+            lo = hi = 0u;
+            if (!(h2 > 0.0f)) return;
+            float h;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(h2));
+            h *= 1.000001f;
+            // shear of x over the part of the square a pair within reach can lie in
+            const float zl = fmaxf(zlo, -fp.reach), zh = fminf(zhi, fp.reach), yl = fmaxf(ylo, -fp.reach), yh = fminf(yhi, fp.reach);
+            const float slo = fminf(t_xy * yl, t_xy * yh) + fminf(t_xz * zl, t_xz * zh);
+            const float shi = fmaxf(t_xy * yl, t_xy * yh) + fmaxf(t_xz * zl, t_xz * zh);
+            const int cl = (int)floorf(c.xc + (-h - shi) * inv_wx - 1e-3f), ch = (int)floorf(c.xc + (h - slo) * inv_wx + 1e-3f);
+            const int el = min(max(cl - a0, 0), next), eh = min(max(ch - a0 + 1, 0), next);
+            lo = eo[el];
+            hi = eo[eh];
+        };
+        (void)wx_f;
 #pragma unroll
         for (int i = 0; i < NRH; ++i) {
             const int r = rlo + i;
@@ -417,10 +467,13 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                     lo = eo[ea];
                     hi = eo[WX] + pos + (has_b ? 1u : 0u);         // the own extended position of the pair's last query
                 } else {
-                    window(q, ea, eo, g, lo, hi);
+                    int dy = 0, dz = 0;
+                    if (MIC == MIC_TRICLINIC) { row_dydz(r, dy, dz); window_tri(cpa, dy, dz, eo, lo, hi); }
+                    else window(q, ea, eo, g, lo, hi);
                     if (has_b) {
                         uint32_t lo2, hi2;
-                        window(qb, eb, eo, g, lo2, hi2);
+                        if (MIC == MIC_TRICLINIC) window_tri(cpb, dy, dz, eo, lo2, hi2);
+                        else window(qb, eb, eo, g, lo2, hi2);
                         if (lo2 < hi2) {
                             if (lo < hi) { lo = min(lo, lo2); hi = max(hi, hi2); }
                             else { lo = lo2; hi = hi2; }
@@ -506,7 +559,7 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
 
 // Walker: stages the rows of its unit (x, y, z planes, extended order) and walks the planner's
 // records, 32 at a time per warp.
-template <bool SELF, class Sink, int CAP, int MIN_CTAS>
+template <bool SELF, class Sink, int CAP, int MIN_CTAS, int MIC = MIC_ORTHO_LAZY>
 __global__ void __launch_bounds__(Sink::THREADS, MIN_CTAS)
 fine_walk_kernel(const float4 *__restrict__ q_atoms, const float4 *__restrict__ c_atoms,
                  const FineUnit<SELF ? 13 : 25> *__restrict__ units, const uint32_t *__restrict__ lists, int list_cap,
@@ -590,7 +643,7 @@ fine_walk_kernel(const float4 *__restrict__ q_atoms, const float4 *__restrict__ 
     }
     if (SELF && sp.include_self && (uint32_t)tid < nq) {           // capped_distance(x, x) reports (i, i)
         const float4 q = q_atoms[qs0 + tid];
-        const double d2 = pair_d2_exact<MIC_ORTHO_LAZY>(q.x, q.y, q.z, q.x, q.y, q.z, box);
+        const double d2 = pair_d2_exact<MIC>(q.x, q.y, q.z, q.x, q.y, q.z, box);
         if (d2 <= sp.d2_max && d2 > sp.d2_min) sink.template hit_w<false>(__float_as_int(q.w), __float_as_int(q.w), d2, f);
     }
     // (constants are read back from shared memory: a kernel parameter would be re-fetched from
@@ -605,7 +658,7 @@ fine_walk_kernel(const float4 *__restrict__ q_atoms, const float4 *__restrict__ 
         const uint32_t n = min(*nslow, (uint32_t)RF_SLOW);
         for (uint32_t i = lane; i < n; i += 32) {
             const uint2 e = slowq[i];
-            quad_exact<SELF, Sink>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, e.x, e.y, f);
+            quad_exact<SELF, Sink, MIC>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, e.x, e.y, f);
         }
         __syncwarp();
         if (lane == 0) *nslow = 0u;
@@ -652,10 +705,10 @@ fine_walk_kernel(const float4 *__restrict__ q_atoms, const float4 *__restrict__ 
             const uint32_t cslot = p < fb.end0 ? fa.g0 + p : (p < fb.end1 ? fa.g1 + (p - fb.end0) : fa.g2 + (p - fb.end1));
             const uint32_t at = atomicAdd(nslow, 1u);
             if (at < (uint32_t)RF_SLOW) slowq[at] = make_uint2(qslot + (uint32_t)which, cslot);
-            else quad_exact<SELF, Sink>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, qslot + (uint32_t)which, cslot, f);
+            else quad_exact<SELF, Sink, MIC>(sink, &box, sp.d2_max, sp.d2_min, q_atoms, c_atoms, qslot + (uint32_t)which, cslot, f);
         };
-        const float3 na3 = make_float3(-qa3.x, -(qa3.y - fc.sy), -(qa3.z - fc.sz));
-        const float3 nb3 = make_float3(-qb3.x, -(qb3.y - fc.sy), -(qb3.z - fc.sz));
+        const float3 na3 = make_float3(MIC == MIC_TRICLINIC ? -(qa3.x - fc.sx) : -qa3.x, -(qa3.y - fc.sy), -(qa3.z - fc.sz));
+        const float3 nb3 = make_float3(MIC == MIC_TRICLINIC ? -(qb3.x - fc.sx) : -qb3.x, -(qb3.y - fc.sy), -(qb3.z - fc.sz));
         if (home)                                                  // candidates behind each query's own position only
             fine_walk2<true, CAP>(tile0, qa, qa + len, na3, nb3, (int)(own0 + qi) - (int)(4u * qa), kc, slow_fn);
         else
