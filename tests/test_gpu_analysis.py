@@ -295,7 +295,7 @@ def test_qcp_trajectory_streamed_kernel(oracle, n, F, weighted):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["ortho_w2", "ortho_w2_ab", "ortho_w2_ab_excl", "ortho_w1", "ortho_w1_ab",
                                   "ortho_perframe", "tric_w1", "tric_w1_ab", "tric_perframe", "tric_flat",
-                                  "tric_w2", "tric_w2_ab", "tric_flat_dense", "tric_perframe_dense"])
+                                  "tric_w2", "tric_w2_ab", "tric_flat_dense", "tric_perframe_dense", "tric_npt_dense"])
 def test_interrdf_row_traversal(oracle, case):
     """The row-staged traversal (csrc/rowtile.cuh): every grid flavour it takes, against
     the oracle's FastNS + np.histogram, bit-exact counts.  The dense triclinic cases have
@@ -326,6 +326,10 @@ def test_interrdf_row_traversal(oracle, case):
         dims = np.tile(np.array([60, 60, 60, 60, 60, 90], dtype=np.float32), (F, 1))
         if case.startswith("tric_flat"):
             dims[:] = np.array([70, 64, 58, 75, 100, 85], dtype=np.float32)
+        if case == "tric_npt_dense":                       # a 60/60/90 cell that breathes: per-frame cells, all of them
+            N = 24000                                      # with a complete reference stencil (8 cells of >= 7.35 A)
+            dims[1, :3] *= 1.03
+            dims[2, :3] *= 1.038
         if case.startswith("tric_perframe"):
             dims[1] = np.array([64, 58, 66, 70, 80, 95], dtype=np.float32)
             dims[2, :3] *= 1.07
