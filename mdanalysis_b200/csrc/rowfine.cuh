@@ -258,16 +258,28 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
         for (int w = tid; w < (int)(sizeof(FrameGeom) / 4); w += T) dst[w] = src[w];
     }
     for (int w = tid; w < NW * NB; w += T) (&s_cnt[0][0])[w] = 0u;
+    // where this CTA is: one thread divides (r02c line profile: the three runtime divisions, done by
+    // every thread, were 5.6 % of the kernel's instructions)
+    __shared__ int s_where[4];                                     // runs, x run, y, z
+    if (tid == 0) {
+        const GridGeom &gg = (per_frame ? fgs + f : &fg_const)->grid;
+        const int runs0 = (gg.ncells[0] + fp.R - 1) / fp.R;
+        const int rest = (int)blockIdx.x / runs0;
+        s_where[0] = runs0;
+        s_where[1] = (int)blockIdx.x - rest * runs0;
+        s_where[2] = rest % gg.ncells[1];
+        s_where[3] = rest / gg.ncells[1];
+    }
     __syncthreads();
     const int WX = fp.WX, R = fp.R;
     const int nx = s_fg.grid.ncells[0], ny = s_fg.grid.ncells[1], nz = s_fg.grid.ncells[2];
-    const int runs = (nx + R - 1) / R;
+    const int runs = s_where[0];
     FineUnit<NR> &unit = units[(uint64_t)f * gridDim.x + blockIdx.x];
     if (blockIdx.x >= (unsigned)(runs * ny * nz)) {                // frames may have fewer cells (uniform)
         if (tid == 0) unit.h.nq = 0u;
         return;
     }
-    const int xr = blockIdx.x % runs, y = (blockIdx.x / runs) % ny, z = blockIdx.x / (runs * ny);
+    const int xr = s_where[1], y = s_where[2], z = s_where[3];
     const int c0h = xr * R, c1h = min(c0h + R, nx), nh = c1h - c0h;
     const int a0 = c0h - WX, next = nh + 2 * WX;                   // staged fine cells [a0, a0 + next)
     const int64_t cbase = per_frame ? s_fg.cell_base : (int64_t)f * s_fg.grid.ncell_total;
@@ -377,15 +389,19 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
         uint32_t *eo = eoff + r * ne1;
         for (int e0 = lane; e0 < ne1; e0 += 128) {
             uint32_t val[4];
+            const int groups = min(4, (ne1 - (e0 - lane) + 31) >> 5);   // uniform: 32-cell groups left in the row
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int a = a0 + min(e0 + 32 * u, ne1 - 1);
-                val[u] = S[a < 0 ? nx + a : (a <= nx ? a : a - nx)];
+                if (u < groups) {
+                    const int a = a0 + min(e0 + 32 * u, ne1 - 1);
+                    val[u] = S[a < 0 ? nx + a : (a <= nx ? a : a - nx)];
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int e = e0 + 32 * u, a = a0 + e;
-                if (e < ne1) eo[e] = min(a < 0 ? val[u] - g0 : (a <= nx ? nL + (val[u] - g1) : nL + nM + (val[u] - g2)), top);
+                if (u < groups && e < ne1)
+                    eo[e] = min(a < 0 ? val[u] - g0 : (a <= nx ? nL + (val[u] - g1) : nL + nM + (val[u] - g2)), top);
             }
         }
     }
@@ -406,7 +422,17 @@ fine_plan_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
             }
             return e0;
         };
-        const int ea = home_cell(pos), eb = has_b ? home_cell(pos + 1u) : ea;
+        // (the cell from the coordinate -- the sort key's own float64 arithmetic may differ by one at a
+        // cell face, so the guess is checked against the cell starts and the search decides otherwise;
+        // the two searches were 6.7 % of the kernel's instructions)
+        auto home_cell_of = [&](const float4 &qq, uint32_t at) {
+            int e = (int)(qq.x * inv_wx) - c0h;
+            if (MIC == MIC_TRICLINIC) e = (int)((qq.x - (float)s_fg.grid.cs[3] * qq.y - (float)s_fg.grid.cs[6] * qq.z) * inv_wx) - c0h;
+            e = min(max(e, 0), nh - 1);
+            const uint32_t slot = qs0 + at;
+            return (s_qraw[e] <= slot && slot < s_qraw[e + 1]) ? e : home_cell(at);
+        };
+        const int ea = has_a ? home_cell_of(q, pos) : 0, eb = has_b ? home_cell_of(qb, pos + 1u) : ea;
         const float reach2 = fp.reach * fp.reach;
         auto window = [&](const float4 &qq, int e0, const uint32_t *eo, const float4 &g, uint32_t &lo, uint32_t &hi) {
             const float gy = fmaf(g.x, qq.y, g.y), gz = fmaf(g.z, qq.z, g.w);
