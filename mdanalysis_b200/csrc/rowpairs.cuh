@@ -69,6 +69,9 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
     const uint32_t rtile = (uint32_t)(rp_dyn_bytes(cap) / (2 * sizeof(float4)));   // candidates per buffer, row-by-row path
     float4 *tile0 = reinterpret_cast<float4 *>(rp_dyn);
     __shared__ uint32_t s_rowbase[ROW_MAXROWS + 1];
+    // plane path: per row, where the runs end in the tile and what turns a tile position of a run into
+    // a global slot; the row's image (ib, ic).  {end of run 0, end of run 1, offset 0, offset 1, offset 2, ib | ic << 8}
+    __shared__ uint32_t s_runs[ROW_MAXROWS][6];
     __shared__ uint32_t s_next;                                     // next unclaimed work item (plane path)
     // plane path: per-lane survivor queues [warp][slot][lane]; row-by-row path: per-warp compacted queues
     constexpr int Q_PLANE = NW * (RP_LQ * 32 * 2 + RP_WQ * 4), Q_ROW = NW * RP_QUEUE * 9;
@@ -153,6 +156,16 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                 px[rb + t] = c.x; py[rb + t] = c.y; pz[rb + t] = c.z;
             }
         }
+        for (int r = tid; r < nrows; r += T) {
+            const RowInfo &ri = bk.row[r];
+            const uint32_t rb = s_rowbase[r];
+            s_runs[r][0] = rb + ri.end[0];
+            s_runs[r][1] = rb + ri.end[1];
+            s_runs[r][2] = ri.g[0] - rb;
+            s_runs[r][3] = ri.g[1] - rb - ri.end[0];
+            s_runs[r][4] = ri.g[2] - rb - ri.end[1];
+            s_runs[r][5] = (uint32_t)(ri.ib + 1) | (uint32_t)(ri.ic + 1) << 8;
+        }
         if (tid < RP_PAD) {                                         // the last trip may read past the end
             const uint32_t e = s_rowbase[nrows] + tid;
             px[e] = py[e] = pz[e] = 1.0e18f;
@@ -201,12 +214,12 @@ row_pairs_kernel(const float4 *__restrict__ q_atoms, const uint32_t *__restrict_
                 if (v0) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e0) : "r"(wq0 + 4u * (first + lane)));
                 if (v1) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e1) : "r"(wq0 + 4u * (first + lane + 32u)));
                 auto locate = [&](uint32_t e, int &ia, int &ib, int &ic) -> uint32_t {
-                    const int r = ra + (int)((e >> 12) & 15u);
-                    const RowInfo &ri = bk.row[r];
-                    const uint32_t t = (e & 4095u) - s_rowbase[r];
-                    const int sx = t >= ri.end[1] ? 2 : (t >= ri.end[0] ? 1 : 0);
-                    ia = 1 - sx; ib = -ri.ib; ic = -ri.ic;
-                    return ri.g[sx] + (t - (sx ? ri.end[sx - 1] : 0u));
+                    const uint32_t *rr = s_runs[ra + (int)((e >> 12) & 15u)];
+                    const uint32_t pos = e & 4095u;
+                    const int sx = pos >= rr[1] ? 2 : (pos >= rr[0] ? 1 : 0);
+                    const uint32_t img = rr[5];
+                    ia = 1 - sx; ib = 1 - (int)(img & 255u); ic = 1 - (int)(img >> 8);
+                    return pos + rr[2 + sx];
                 };
                 int a0 = 0, b0 = 0, g0 = 0, a1 = 0, b1 = 0, g1 = 0;
                 const uint32_t s0 = locate(e0, a0, b0, g0), s1 = locate(e1, a1, b1, g1);
